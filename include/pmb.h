@@ -1,0 +1,148 @@
+/* pmb.h -- C ABI of libpmb.so: the B200 (sm_100a) hot path of pyMOTO's compliance design iteration.
+ *
+ * Every entry point replaces one numpy/scipy call site of the reference (pyMOTO v2.0.1, paths relative to
+ * /root/reference) and is what a ctypes binding in the reference would call:
+ *
+ *   pmb_csr_pattern      pymoto/modules/assembly.py:130-206   (argsort/unique pattern build -> closed form)
+ *   pmb_assemble         pymoto/modules/assembly.py:255-275   (np.add.at scatter, bc rows/cols, bc diagonal)
+ *   pmb_assemble_sens    pymoto/modules/assembly.py:298-315 -> pymoto/common/dyadcarrier.py:408-412 (einsum)
+ *   pmb_rowstats         pymoto/solvers/solvers.py:88-96      (get_diagonal_indices) + iterative.py:38-39 (diagonal)
+ *   pmb_spmv             scipy csr_matvec at pymoto/solvers/iterative.py:236-255,359,375,382, solvers.py:84,237
+ *   pmb_smooth0          pymoto/solvers/iterative.py:43,233-234   (u = w r/D)
+ *   pmb_restrict         pymoto/solvers/iterative.py:244      (R^T r, csc_matvec)
+ *   pmb_prolong_add      pymoto/solvers/iterative.py:250      (u += R u_c, csr_matvec)
+ *   pmb_galerkin         pymoto/solvers/iterative.py:173      (R^T A R, csr_matmat x2)
+ *   pmb_densify / pmb_dense_invert / pmb_dense_gemv
+ *                        pymoto/solvers/sparse.py:533-550     (splu + solve on the coarsest operator)
+ *   pmb_dots / pmb_lincomb / pmb_cg_xr_update
+ *                        pymoto/solvers/iterative.py:376-395  (CG dot products and vector updates)
+ *   pmb_bc_split         pymoto/solvers/solvers.py:175-176    (Dirichlet dofs: u = f/diag, rhs zeroed)
+ *   pmb_filter_apply / pmb_vec_div
+ *                        pymoto/modules/filter.py:266-270     (csc_matvec of H, division by Hs)
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; pmb_last_error() gives the (thread-local) message.
+ *     Nothing throws across this boundary and nothing calls exit().
+ *   - all array arguments are DEVICE pointers owned by the caller (FP64 unless stated); the library never frees
+ *     them.  `stream` is a cudaStream_t passed as void*.
+ *   - matrices are passed as the CSR `data` array only: on a structured voxel grid the CSR pattern is a closed
+ *     form of (nx, ny, nz, ndof) (27-/9-point block stencil, rows and columns in node-major dof order), so
+ *     `indptr`/`indices` are never read by the solver kernels.  pmb_csr_pattern materialises them bit-exactly
+ *     for export.  `data` must be 16-byte aligned and padded by 2 doubles.
+ *   - slab decomposition (multi-GPU): a rank owns node planes [kz0, kz0+nzl).  Nodal vectors, the bc mask and
+ *     matrix rows are addressed relative to the first OWNED plane; halo planes kz0-1 and kz0+nzl are read at
+ *     negative / past-the-end offsets and must be valid memory.  One GPU: kz0 = 0, nzl = nz+1.
+ */
+#ifndef PMB_H
+#define PMB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int nx, ny, nz; /* elements per direction; nz = 0 means 2-D (quad4)            */
+  int ndof;       /* dofs per node, 1..3                                          */
+  int kz0;        /* first owned node plane                                       */
+  int nzl;        /* number of owned node planes                                  */
+} pmb_grid;
+
+/* coefficient c * (*num) / (*den or sqrt(*den)); num/den may be NULL (-> 1) and live in device memory */
+typedef struct {
+  double c;
+  const double* num;
+  const double* den;
+  int sqrt_den;
+} pmb_coef;
+
+enum { PMB_SPMV = 0, PMB_RESIDUAL = 1, PMB_JACOBI = 2 };
+
+const char* pmb_last_error(void);
+int pmb_version(void);
+
+/* number of matrix entries / rows owned by this slab */
+long long pmb_nnz(const pmb_grid* g);
+long long pmb_nrows(const pmb_grid* g);
+
+/* K0: CSR pattern.  index_bits = 32 or 64 selects the integer type of indptr (nrows+1) and indices (nnz). */
+int pmb_csr_pattern(const pmb_grid* g, void* indptr, void* indices, int index_bits, void* stream);
+
+/* K1: data = sum_e x_e Ke (sequential adds from 0.0 in ascending element number, no FMA: bit-exact with
+ * np.add.at), rows/cols in bcmask (1 byte per dof, may be NULL) zeroed, bc diagonal = bcdiagval.
+ * x points at element layer kz0 (layer kz0-1 is read as halo when kz0 > 0). Ke is (nn*ndof)^2 row-major. */
+int pmb_assemble(const pmb_grid* g, const double* Ke, const double* x, const unsigned char* bcmask,
+                 double bcdiagval, double* data, void* stream);
+
+/* K11: dx_e = sum_{a,b} u[dof(e,a)] Ke[a,b] v[dof(e,b)], u and v taken as 0 at masked dofs.
+ * Element layers [kz0, min(kz0+nzl, nz)) are produced (all elements in 2-D). accumulate != 0 adds into dx. */
+int pmb_assemble_sens(const pmb_grid* g, const double* Ke, const double* u, const double* v,
+                      const unsigned char* bcmask, double* dx, int accumulate, void* stream);
+
+/* diag[r] = A[r,r]; nnz_offdiag[r] = number of non-zero off-diagonal entries in row r (int32). Either may be NULL. */
+int pmb_rowstats(const pmb_grid* g, const double* data, double* diag, int* nnz_offdiag, void* stream);
+
+/* K2/K3: y = A x | y = b - A x | y = x + w (b - A x)/diag.   y must not alias x.
+ * dot_out (may be NULL): 3 doubles, receives sum_r y_r x_r, sum_r x_r dotv_r and sum_r y_r dotv_r over the
+ * owned rows (the last two only when dotv != NULL); ws is a workspace of at least pmb_spmv_ws_doubles(g)
+ * doubles used for the deterministic two-stage reduction. */
+int pmb_spmv(const pmb_grid* g, int mode, const double* data, const double* x, const double* b,
+             const double* diag, double w, double* y, const double* dotv, double* dot_out, double* ws,
+             void* stream);
+long long pmb_spmv_ws_doubles(const pmb_grid* g);
+/* workspace (doubles, zero-initialised by the caller once) for pmb_dots / pmb_cg_xr_update */
+long long pmb_ws_doubles(void);
+
+/* u = w * (r / diag) */
+int pmb_smooth0(long long n, double w, const double* r, const double* diag, double* u, void* stream);
+
+/* K4: rc = R^T rf.  gf = fine grid (its kz0/nzl describe the fine slab), gc = coarse grid (coarse slab). */
+int pmb_restrict(const pmb_grid* gf, const pmb_grid* gc, const double* rf, double* rc, void* stream);
+/* K5: uf += R uc */
+int pmb_prolong_add(const pmb_grid* gf, const pmb_grid* gc, const double* uc, double* uf, void* stream);
+/* K6: Ac = R^T A R in the coarse grid's own stencil-CSR layout */
+int pmb_galerkin(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* Ac, void* stream);
+
+/* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (Gauss-Jordan without
+ * pivoting, valid for SPD); scratch holds 2n doubles; info (device int) is set non-zero on a non-positive pivot. */
+int pmb_densify(const pmb_grid* g, const double* data, double* dense, void* stream);
+int pmb_dense_invert(int n, double* dense, double* scratch, int* info, void* stream);
+int pmb_dense_gemv(int n, const double* M, const double* x, double* y, void* stream);
+
+/* K8: out[i] = sum a_i . b_i for i < k (k <= 4), deterministic (fixed partial order). */
+int pmb_dots(long long n, int k, const double* a0, const double* b0, const double* a1, const double* b1,
+             const double* a2, const double* b2, const double* a3, const double* b3, double* out, double* ws,
+             void* stream);
+
+/* K9: out = ca*a + cb*b (b may be NULL); coefficients may reference device scalars. out may alias a or b. */
+int pmb_lincomb(long long n, double* out, pmb_coef ca, const double* a, pmb_coef cb, const double* b,
+                void* stream);
+/* fused CG update: alpha = (*pr)/(*pq); x += alpha p; if q != NULL: r -= alpha q and rr_out = r.r */
+int pmb_cg_xr_update(long long n, double* x, double* r, const double* p, const double* q, const double* pr,
+                     const double* pq, double* rr_out, double* ws, void* stream);
+
+/* Dirichlet split: sol = mask ? rhs/diag : 0 ; rhs_loc = mask ? 0 : rhs (mask: 1 byte per dof) */
+int pmb_bc_split(long long n, const unsigned char* mask, const double* rhs, const double* diag, double* sol,
+                 double* rhs_loc, void* stream);
+/* mask[r] = (diag[r] != 0 && nnz_offdiag[r] == 0): rows whose only non-zero is the diagonal */
+int pmb_diag_mask(long long n, const double* diag, const int* nnz_offdiag, unsigned char* mask, void* stream);
+/* out = mask ? 0 : in */
+int pmb_mask_zero(long long n, const unsigned char* mask, const double* in, double* out, void* stream);
+
+/* K10: density filter stencil. wtab is the (2d+1)^3 ((2d+1)^2 in 2-D) weight table, z-major, x fastest.
+ * out[e] = (sum_j w_ij in[j]) / (hs ? hs[e] : 1) over the window clipped to the domain, accumulated in
+ * ascending element number with separate multiply and add (bit-exact with scipy csc_matvec).
+ * in == NULL means in = 1 (row sums Hs).  Element layers [ez0, ez0+nezl) are produced; `in`, `hs`, `out`
+ * point at layer ez0 and `in` is read d layers beyond on each side where those exist in the domain. */
+int pmb_filter_apply(const pmb_grid* g, int ez0, int nezl, int d, const double* wtab, const double* in,
+                     const double* hs, double* out, void* stream);
+/* out = a / b */
+int pmb_vec_div(long long n, const double* a, const double* b, double* out, void* stream);
+
+/* SIMP glue kept on device for the resident path: s = xmin + (1-xmin) y^p ; dy = ds * p (1-xmin) y^(p-1) */
+int pmb_simp(long long n, double xmin, int p, const double* y, double* s, void* stream);
+int pmb_simp_bwd(long long n, double xmin, int p, const double* y, const double* ds, double* dy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,112 @@
+"""ctypes binding of libpmb.so (the C ABI declared in include/pmb.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.  The library is
+built in-tree by ``pymoto_b200/_build.py`` (``__graft_entry__.build()``) with nvcc for sm_100a.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmb.so")
+
+
+class PmbError(RuntimeError):
+    pass
+
+
+class Grid(C.Structure):
+    """Mirror of ``pmb_grid`` (include/pmb.h)."""
+
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("ndof", C.c_int), ("kz0", C.c_int), ("nzl", C.c_int)]
+
+    def __repr__(self):
+        return f"Grid({self.nx}x{self.ny}x{self.nz}, ndof={self.ndof}, planes=[{self.kz0},{self.kz0 + self.nzl}))"
+
+
+class Coef(C.Structure):
+    """Mirror of ``pmb_coef``: c * (*num) / (*den or sqrt(*den))."""
+
+    _fields_ = [("c", C.c_double), ("num", C.c_void_p), ("den", C.c_void_p), ("sqrt_den", C.c_int)]
+
+
+def coef(c=1.0, num=None, den=None, sqrt_den=False):
+    return Coef(float(c), num, den, 1 if sqrt_den else 0)
+
+
+_P = C.c_void_p
+_LL = C.c_longlong
+_D = C.c_double
+_I = C.c_int
+_G = C.POINTER(Grid)
+
+# name -> (restype, argtypes); every symbol include/pmb.h declares
+SIGNATURES = {
+    "pmb_last_error": (C.c_char_p, []),
+    "pmb_version": (_I, []),
+    "pmb_nnz": (_LL, [_G]),
+    "pmb_nrows": (_LL, [_G]),
+    "pmb_csr_pattern": (_I, [_G, _P, _P, _I, _P]),
+    "pmb_assemble": (_I, [_G, _P, _P, _P, _D, _P, _P]),
+    "pmb_assemble_sens": (_I, [_G, _P, _P, _P, _P, _P, _I, _P]),
+    "pmb_rowstats": (_I, [_G, _P, _P, _P, _P]),
+    "pmb_spmv": (_I, [_G, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
+    "pmb_spmv_ws_doubles": (_LL, [_G]),
+    "pmb_ws_doubles": (_LL, []),
+    "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
+    "pmb_restrict": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_prolong_add": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_galerkin": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_densify": (_I, [_G, _P, _P, _P]),
+    "pmb_dense_invert": (_I, [_I, _P, _P, _P, _P]),
+    "pmb_dense_gemv": (_I, [_I, _P, _P, _P, _P]),
+    "pmb_dots": (_I, [_LL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pmb_lincomb": (_I, [_LL, _P, Coef, _P, Coef, _P, _P]),
+    "pmb_cg_xr_update": (_I, [_LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pmb_bc_split": (_I, [_LL, _P, _P, _P, _P, _P, _P]),
+    "pmb_diag_mask": (_I, [_LL, _P, _P, _P, _P]),
+    "pmb_mask_zero": (_I, [_LL, _P, _P, _P, _P]),
+    "pmb_filter_apply": (_I, [_G, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
+    "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
+    "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),
+}
+
+SPMV, RESIDUAL, JACOBI = 0, 1, 2
+
+_lib = None
+launch_count = 0  # number of libpmb kernel-launching calls made (bench.py reports it)
+
+
+def load():
+    """Load libpmb.so; raises PmbError when it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PmbError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). pymoto_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise PmbError with pmb_last_error() on failure."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        raise PmbError(f"{name} failed: {lib.pmb_last_error().decode()}")
+
+
+def query(name, *args):
+    lib = load()
+    v = getattr(lib, name)(*args)
+    if v < 0:
+        raise PmbError(f"{name} failed: {lib.pmb_last_error().decode()}")
+    return v

@@ -1,0 +1,178 @@
+"""Assembly modules with the reference's constructor signatures, producing a DeviceCSR on the GPU.
+
+Mirrors pymoto/modules/assembly.py: ``AssembleGeneral`` (:18-315), ``AssembleStiffness`` (:407-463),
+``AssemblePoisson`` (:523-560).  The reference precomputes a CSR pattern and a scatter map (:100-230) and runs
+``np.add.at`` per call (:255-275); here the pattern is closed-form and the values are written by
+``pmb_assemble`` (bit-identical values, see pmb_assembly.cu).  Backward: ``pmb_assemble_sens`` (:298-315).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as dv
+from .core import Module
+from .domain import grid_dims
+from .dyad import DeviceDyad
+from .matrix import DeviceCSR, make_grid
+
+
+def _strain_displacement(dN_dx):
+    """B in Voigt order [xx, yy, zz, yz, zx, xy] (3-D) / [xx, yy, xy] (2-D); cf. get_B, assembly.py:318-370."""
+    dim, nn = dN_dx.shape
+    B = np.zeros((dim * (dim + 1) // 2, nn * dim), dtype=dN_dx.dtype)
+    for a in range(nn):
+        c = a * dim
+        if dim == 2:
+            B[0, c], B[1, c + 1] = dN_dx[0, a], dN_dx[1, a]
+            B[2, c], B[2, c + 1] = dN_dx[1, a], dN_dx[0, a]
+        elif dim == 3:
+            B[0, c], B[1, c + 1], B[2, c + 2] = dN_dx[0, a], dN_dx[1, a], dN_dx[2, a]
+            B[3, c + 1], B[3, c + 2] = dN_dx[2, a], dN_dx[1, a]
+            B[4, c], B[4, c + 2] = dN_dx[2, a], dN_dx[0, a]
+            B[5, c], B[5, c + 1] = dN_dx[1, a], dN_dx[0, a]
+        else:
+            raise ValueError(f"Number of dimensions ({dim}) must be 2 or 3")
+    return B
+
+
+def _elasticity_matrix(E, nu, mode):
+    """cf. get_D, assembly.py:373-404."""
+    mu = E / (2 * (1 + nu))
+    lam = (E * nu) / ((1 + nu) * (1 - 2 * nu))
+    c1 = 2 * mu + lam
+    if "strain" in mode:
+        return np.array([[c1, lam, 0], [lam, c1, 0], [0, 0, mu]])
+    if "stress" in mode:
+        return E / (1 - nu * nu) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]])
+    if "3d" in mode:
+        D = np.zeros((6, 6))
+        D[:3, :3] = lam
+        D[np.arange(3), np.arange(3)] = c1
+        D[np.arange(3, 6), np.arange(3, 6)] = mu
+        return D
+    raise ValueError("Only for plane-stress, plane-strain, or 3d")
+
+
+def _gauss_points(domain):
+    siz = domain.element_size
+    for n in domain.node_numbering:
+        yield np.asarray(n) * (siz / 2) / np.sqrt(3)
+
+
+class AssembleGeneral(Module):
+    r"""``A = sum_e x_e A_e`` on a structured grid, Dirichlet rows/columns zeroed with ``bcdiagval`` on the diagonal.
+
+    Input: ``x`` scaling vector of size ``(nel)`` (numpy array or CUDA tensor).  Output: :class:`DeviceCSR`.
+    """
+
+    def __init__(self, domain, element_matrix, bc=None, bcdiagval=None, matrix_type=None, add_constant=None,
+                 reuse_sparsity: bool = True):
+        elmats = list(element_matrix) if isinstance(element_matrix, (list, tuple)) else [element_matrix]
+        self.elmat = [np.asarray(m) for m in elmats]
+        self.nmat = len(self.elmat)
+        if self.nmat < 1:
+            raise ValueError("No or invalid element-matrix is given")
+        if self.nmat > 1:
+            raise NotImplementedError("pymoto_b200.AssembleGeneral supports one element matrix per module")
+        Ke = self.elmat[0]
+        if np.iscomplexobj(Ke):
+            raise TypeError("complex element matrices are not supported by the B200 hot path (real FP64 only)")
+        elemnodes = domain.elemnodes
+        if Ke.shape[0] % elemnodes != 0:
+            raise ValueError("Number of rows in element matrix should be a multiple of the number of nodes per element")
+        if Ke.shape[1] % elemnodes != 0:
+            raise ValueError("Number of cols in element matrix should be a multiple of the number of nodes per element")
+        self.mdof = Ke.shape[0] // elemnodes
+        self.ndof = Ke.shape[1] // elemnodes
+        if self.mdof != self.ndof:
+            raise NotImplementedError("pymoto_b200.AssembleGeneral supports square matrices only")
+        if not 1 <= self.ndof <= 3:
+            raise NotImplementedError("pymoto_b200 supports 1..3 dofs per node")
+        if matrix_type is not None and getattr(matrix_type, "__name__", "") not in ("csr_matrix", "csr_array", "DeviceCSR"):
+            raise NotImplementedError("pymoto_b200 assembles CSR (DeviceCSR) only")
+        if add_constant is not None:
+            raise NotImplementedError("add_constant is not supported by the B200 hot path")
+        self.domain = domain
+        self.nel = domain.nel
+        self.m = self.n = self.ndof * domain.nnodes
+        self.reuse_sparsity = reuse_sparsity  # the pattern is closed-form: nothing to precompute
+
+        dv.require_cuda()
+        nx, ny, nz = grid_dims(domain)
+        self.grid = make_grid(nx, ny, nz, self.ndof)
+        self._Ke_dev = dv.to_device(np.ascontiguousarray(Ke, dtype=np.float64).ravel())
+
+        self.bc = None
+        self.bcdiagval = bcdiagval
+        self._bcmask = None
+        if bc is not None:
+            self.bc = np.asarray(bc).ravel()
+            if bcdiagval is None:
+                self.bcdiagval = np.max(Ke)  # assembly.py:94-98
+            mask = np.zeros(self.n, dtype=np.uint8)
+            mask[self.bc] = 1
+            self._bcmask = dv.to_device(mask, torch.uint8)
+        self._mat = None
+
+    def __call__(self, xscale):
+        n = xscale.numel() if isinstance(xscale, torch.Tensor) else np.size(xscale)
+        if n != self.nel:
+            raise ValueError(f"Input vector wrong size ({n}), must be equal to #nel ({self.nel})")
+        self._x_on_device = dv.is_device(xscale)
+        x = dv.to_device(xscale).reshape(-1)
+        # a fresh value buffer each call would cost 8*nnz bytes of allocation per design iteration; the matrix
+        # object is reused and its cached row statistics dropped (consumers re-read it on every update()).
+        if self._mat is None:
+            self._mat = DeviceCSR(self.grid, bc_mask=self._bcmask)
+        mat = self._mat
+        _lib.call("pmb_assemble", self.grid, dv.ptr(self._Ke_dev), dv.ptr(x), dv.ptr(self._bcmask),
+                  float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
+        mat.invalidate()
+        return mat
+
+    def _sensitivity(self, dgdmat):
+        if dgdmat is None or getattr(dgdmat, "size", 1) <= 0:
+            return [None]
+        if not isinstance(dgdmat, DeviceDyad):
+            raise TypeError("pymoto_b200.AssembleGeneral back-propagates a DeviceDyad (from pymoto_b200.LinSolve)")
+        dx = dv.zeros(self.nel)
+        first = True
+        for u, v in zip(dgdmat.u, dgdmat.v):
+            _lib.call("pmb_assemble_sens", self.grid, dv.ptr(self._Ke_dev), dv.ptr(u), dv.ptr(v), dv.ptr(self._bcmask),
+                      dv.ptr(dx), 0 if first else 1, dv.stream())
+            first = False
+        return [dx if getattr(self, "_x_on_device", False) else dx.cpu().numpy()]
+
+
+class AssembleStiffness(AssembleGeneral):
+    r"""Stiffness matrix ``K = sum_e x_e K_e`` for quad4 / hex8 linear elasticity (assembly.py:407-463)."""
+
+    def __init__(self, domain, *args, e_modulus: float = 1.0, poisson_ratio: float = 0.3, plane="strain", **kwargs):
+        self.E, self.nu = e_modulus, poisson_ratio
+        D = _elasticity_matrix(self.E, self.nu, "3d" if domain.dim == 3 else plane.lower())
+        nd = (2 ** domain.dim) * domain.dim
+        self.stiffness_element = np.zeros((nd, nd))
+        siz = domain.element_size
+        w = np.prod(siz[: domain.dim] / 2)
+        if domain.dim == 2:
+            w *= siz[2]  # thickness
+        for pos in _gauss_points(domain):
+            B = _strain_displacement(domain.eval_shape_fun_der(pos))
+            self.stiffness_element += w * B.T @ D @ B
+        super().__init__(domain, self.stiffness_element, *args, **kwargs)
+
+
+class AssemblePoisson(AssembleGeneral):
+    r"""Scalar diffusion matrix ``P = sum_e x_e P_e`` (thermal conduction etc., assembly.py:523-560)."""
+
+    def __init__(self, domain, *args, material_property: float = 1.0, **kwargs):
+        self.material_property = material_property
+        self.poisson_element = np.zeros((domain.elemnodes, domain.elemnodes))
+        siz = domain.element_size
+        w = np.prod(siz[: domain.dim] / 2)
+        if domain.dim != 3:
+            self.material_property *= siz[domain.dim:]
+        for pos in _gauss_points(domain):
+            Bn = domain.eval_shape_fun_der(pos)
+            self.poisson_element += w * self.material_property * Bn.T @ Bn
+        super().__init__(domain, self.poisson_element, *args, **kwargs)

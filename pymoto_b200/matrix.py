@@ -1,0 +1,115 @@
+"""DeviceCSR: the assembled system matrix as it lives in HBM.
+
+It is the reference's CSR matrix (``csr_matrix((data, indices, indptr))``, pymoto/modules/assembly.py:275) with
+the ``data`` array resident on the GPU.  On a structured voxel grid ``indptr``/``indices`` are a closed form of
+the grid, so they are only materialised (bit-exactly, int32 when nnz fits like scipy's downcast) when a user asks
+for them: ``.indptr``, ``.indices`` or ``.tocsr()``.  The solver kernels stream ``data`` alone.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as dv
+
+
+def make_grid(nx, ny, nz, ndof, kz0=0, nzl=None):
+    return _lib.Grid(int(nx), int(ny), int(nz), int(ndof), int(kz0), int(nz + 1 if nzl is None else nzl))
+
+
+class DeviceCSR:
+    def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None):
+        dv.require_cuda()
+        self.grid = grid
+        self.nnz = _lib.query("pmb_nnz", grid)
+        self.n = _lib.query("pmb_nrows", grid)
+        self.shape = (self.n, self.n)
+        self.ndim = 2
+        self.dtype = np.dtype(np.float64)
+        if data is None:
+            data = dv.empty(self.nnz + 2)  # +2: 16-byte slack read by the 128-bit streaming loads
+            data[self.nnz:] = 0.0
+        assert data.is_cuda and data.dtype == torch.float64 and data.numel() >= self.nnz + 2
+        assert data.data_ptr() % 16 == 0
+        self._buf = data
+        self.bc_mask = bc_mask  # uint8 per dof or None (set by the assembly module; informational)
+        self._indptr = self._indices = None
+        self._diag = self._nnz_off = None
+
+    # ---- values
+    @property
+    def data(self):
+        return self._buf[: self.nnz]
+
+    def invalidate(self):
+        """Call after the values changed in place."""
+        self._diag = self._nnz_off = None
+
+    # ---- row statistics: diagonal + number of non-zero off-diagonals, one pass over the values
+    def rowstats(self):
+        if self._diag is None:
+            self._diag = dv.empty(self.n)
+            self._nnz_off = dv.empty(self.n, torch.int32)
+            _lib.call("pmb_rowstats", self.grid, dv.ptr(self._buf), dv.ptr(self._diag), dv.ptr(self._nnz_off), dv.stream())
+        return self._diag, self._nnz_off
+
+    def diagonal_device(self):
+        return self.rowstats()[0]
+
+    def diagonal(self):
+        return self.diagonal_device().cpu().numpy()
+
+    # ---- products
+    def apply(self, mode, x, y, b=None, diag=None, w=0.0, dotv=None, dot_out=None):
+        """Raw kernel call on device tensors: y = A x | b - A x | x + w (b - A x)/diag, optional fused dots."""
+        ws = None
+        if dot_out is not None:
+            ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles", self.grid))
+        _lib.call("pmb_spmv", self.grid, mode, dv.ptr(self._buf), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y),
+                  dv.ptr(dotv), dv.ptr(dot_out), dv.ptr(ws), dv.stream())
+        return y
+
+    def matvec_device(self, x, out=None):
+        y = dv.empty(self.n) if out is None else out
+        return self.apply(_lib.SPMV, x, y)
+
+    def __matmul__(self, x):
+        xd = dv.to_device(x)
+        if xd.ndim == 1:
+            return dv.like_input(self.matvec_device(xd), x)
+        cols = [self.matvec_device(xd[:, i].contiguous()) for i in range(xd.shape[1])]
+        return dv.like_input(torch.stack(cols, dim=1), x)
+
+    dot = __matmul__
+
+    # ---- export (parity / interop only; never used by the solver path)
+    def _pattern(self):
+        if self._indptr is None:
+            g = self.grid
+            if g.kz0 != 0 or g.nzl != g.nz + 1:
+                raise _lib.PmbError("CSR export needs the whole grid on one rank")
+            bits = 32 if self.nnz < 2 ** 31 - 1 else 64
+            tdt = torch.int32 if bits == 32 else torch.int64
+            self._indptr = dv.empty(self.n + 1, tdt)
+            self._indices = dv.empty(self.nnz, tdt)
+            _lib.call("pmb_csr_pattern", g, dv.ptr(self._indptr), dv.ptr(self._indices), bits, dv.stream())
+        return self._indptr, self._indices
+
+    @property
+    def indptr(self):
+        return self._pattern()[0]
+
+    @property
+    def indices(self):
+        return self._pattern()[1]
+
+    def tocsr(self):
+        import scipy.sparse as sps
+
+        indptr, indices = self._pattern()
+        return sps.csr_matrix((self.data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=self.shape)
+
+    def toarray(self):
+        return self.tocsr().toarray()
+
+    def __repr__(self):
+        return f"DeviceCSR({self.shape[0]}x{self.shape[1]}, nnz={self.nnz}, {self.grid})"

@@ -1,0 +1,416 @@
+"""Linear solvers of the hot path on the GPU: LDAS wrapper, PCG, geometric multigrid, damped Jacobi, and the
+dense coarsest-level solver.
+
+Mirrors the ``LinearSolver`` plug-in API of the reference (pymoto/solvers/solvers.py:6-50: ``update(A)``,
+``solve(rhs, x0=None, trans="N")``) and the classes
+
+  LDAWrapper           pymoto/solvers/solvers.py:99-306
+  DampedJacobi         pymoto/solvers/iterative.py:21-47
+  GeometricMultigrid   pymoto/solvers/iterative.py:124-256
+  CG                   pymoto/solvers/iterative.py:295-403
+
+with the same constructor signatures and the same iteration (so iteration counts match the reference).  All
+vectors inside the solvers are CUDA tensors; ``solve`` accepts numpy arrays or CUDA tensors and returns the same
+kind.  The matrices are :class:`DeviceCSR` (real, symmetric), so ``trans`` in {"N", "T", "H"} all solve the same
+system; anything else raises ``TypeError`` like the reference.
+"""
+import time
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as dv
+from .domain import VoxelDomain, grid_dims
+from .matrix import DeviceCSR, make_grid
+
+
+def _check_trans(trans):
+    if trans not in ("N", "T", "H"):
+        raise TypeError("Only N, T, or H transposition is possible")
+
+
+def _check_matrix(A, who):
+    if not isinstance(A, DeviceCSR):
+        raise TypeError(f"{who} works on a pymoto_b200.DeviceCSR (got {type(A).__name__}); there is no CPU fallback")
+
+
+class LinearSolver:
+    """Base class (pymoto/solvers/solvers.py:6-50)."""
+
+    defined = True
+    _err_msg = ""
+
+    def __init__(self, A=None):
+        if A is not None:
+            self.update(A)
+
+    def update(self, A):
+        raise NotImplementedError(f"Solver not implemented {self._err_msg}")
+
+    def solve(self, rhs, x0=None, trans="N"):
+        raise NotImplementedError(f"Solver not implemented {self._err_msg}")
+
+    @staticmethod
+    def residual(A, x, b, trans="N"):
+        """Relative residual |A x - b| / |b| (|b| = 0 -> absolute), pymoto/solvers/solvers.py:52-85."""
+        _check_trans(trans)
+        xd, bd = dv.to_device(x).reshape(-1), dv.to_device(b).reshape(-1)
+        assert xd.shape == bd.shape
+        r = dv.empty(bd.numel())
+        A.apply(_lib.RESIDUAL, xd, r, b=bd)
+        d = dv.dots([(r, r), (bd, bd)]).cpu().numpy()
+        bnorm = np.sqrt(d[1]) if d[1] != 0 else 1.0
+        return float(np.sqrt(d[0]) / bnorm)
+
+
+class Preconditioner(LinearSolver):
+    """Identity preconditioner (pymoto/solvers/iterative.py:11-18)."""
+
+    def update(self, A):
+        pass
+
+    def solve(self, rhs, x0=None, trans="N"):
+        return rhs.clone() if isinstance(rhs, torch.Tensor) else rhs.copy()
+
+
+class DampedJacobi(Preconditioner):
+    r"""``M = D / w`` (pymoto/solvers/iterative.py:21-47)."""
+
+    def __init__(self, A=None, w=1.0):
+        assert 0 < w <= 1, "w must be between 0 and 1"
+        self.w = w
+        self.D = None
+        super().__init__(A)
+
+    def update(self, A):
+        _check_matrix(A, "DampedJacobi")
+        self.D = A.diagonal_device()
+
+    def solve(self, rhs, x0=None, trans="N"):
+        _check_trans(trans)
+        r = dv.to_device(rhs).reshape(-1)
+        u = dv.empty(r.numel())
+        _lib.call("pmb_smooth0", r.numel(), float(self.w), dv.ptr(r), dv.ptr(self.D), dv.ptr(u), dv.stream())
+        return dv.like_input(u, rhs)
+
+
+class SolverDenseInverse(LinearSolver):
+    """Coarsest-level direct solver: explicit FP64 inverse of the (small, SPD) coarse operator, applied as a GEMV.
+
+    Stands where the reference's ``auto_determine_solver`` puts a sparse LU (pymoto/solvers/iterative.py:174-176,
+    pymoto/solvers/sparse.py:533-550); 675 x 675 for the 3-D elasticity configurations.
+    """
+
+    max_size = 8192
+
+    def __init__(self, A=None):
+        self.n = 0
+        self.inv = None
+        super().__init__(A)
+
+    def update(self, A):
+        _check_matrix(A, "SolverDenseInverse")
+        n = A.shape[0]
+        if n > self.max_size:
+            raise ValueError(f"Coarsest multigrid level has {n} dofs, too many for the dense direct solve "
+                             f"(max {self.max_size}); add GeometricMultigrid levels")
+        if self.inv is None or self.n != n:
+            self.n = n
+            self.inv = dv.empty(n * n)
+            self._scratch = dv.empty(2 * n)
+            self._info = dv.zeros(1, torch.int32)
+            self._out = dv.empty(n)
+        st = dv.stream()
+        _lib.call("pmb_densify", A.grid, dv.ptr(A._buf), dv.ptr(self.inv), st)
+        _lib.call("pmb_dense_invert", n, dv.ptr(self.inv), dv.ptr(self._scratch), dv.ptr(self._info), st)
+        self._checked = False
+
+    def _check_info(self):
+        if not self._checked:
+            info = int(self._info.item())
+            if info != 0:
+                raise np.linalg.LinAlgError(f"coarsest-level operator is not positive definite (pivot {info - 1})")
+            self._checked = True
+
+    def solve(self, rhs, x0=None, trans="N"):
+        _check_trans(trans)
+        r = dv.to_device(rhs).reshape(-1)
+        out = self._out if dv.is_device(rhs) else dv.empty(self.n)
+        _lib.call("pmb_dense_gemv", self.n, dv.ptr(self.inv), dv.ptr(r), dv.ptr(out), dv.stream())
+        return dv.like_input(out, rhs)
+
+
+class GeometricMultigrid(Preconditioner):
+    """Geometric multigrid preconditioner, one V-cycle per ``solve`` (pymoto/solvers/iterative.py:124-256).
+
+    Trilinear prolongation (weights 1, 1/2, 1/4, 1/8, no Dirichlet awareness), restriction = its transpose,
+    Galerkin coarse operator rebuilt on every ``update``, ``smooth_steps`` damped-Jacobi sweeps before and after
+    the coarse correction (the first pre-sweep starts from zero: ``u = w r / D``).
+    """
+
+    _available_cycles = ["v", "w"]
+
+    def __init__(self, domain, A=None, cycle: str = "V", inner_level: LinearSolver = None, smoother: LinearSolver = None,
+                 smooth_steps: int = 5):
+        nx, ny, nz = grid_dims(domain)
+        assert nx % 2 == 0 and ny % 2 == 0 and nz % 2 == 0, f"Domain sizes {nx, ny, nz} must be divisible by 2"
+        self.domain = domain
+        self.A = None
+        assert cycle.lower() in self._available_cycles, f"Cycle ({cycle}) is not available. Options are {self._available_cycles}"
+        self.cycle = cycle
+        self.inner_level = inner_level
+        self.smoother = DampedJacobi(w=0.5) if smoother is None else smoother
+        if not isinstance(self.smoother, DampedJacobi):
+            raise TypeError("pymoto_b200.GeometricMultigrid smooths with DampedJacobi (fused sweep kernel) only")
+        self.smooth_steps = smooth_steps
+        self.sub_domain = VoxelDomain(nx // 2, ny // 2, nz // 2, domain.unitx * 2, domain.unity * 2, domain.unitz * 2)
+        self.Ac = None
+        self._buf = None
+        super().__init__(A)
+
+    def update(self, A):
+        _check_matrix(A, "GeometricMultigrid")
+        g = A.grid
+        nx, ny, nz = grid_dims(self.domain)
+        if (g.nx, g.ny, g.nz) != (nx, ny, nz):
+            raise ValueError(f"Matrix grid {(g.nx, g.ny, g.nz)} does not match the multigrid domain {(nx, ny, nz)}")
+        self.A = A
+        self.smoother.update(A)
+        if self.Ac is None or self.Ac.grid.ndof != g.ndof:
+            self.Ac = DeviceCSR(make_grid(nx // 2, ny // 2, nz // 2, g.ndof))
+            n, nc = A.shape[0], self.Ac.shape[0]
+            self._buf = dict(u=dv.empty(n), u2=dv.empty(n), t=dv.empty(n), rc=dv.empty(nc))
+        _lib.call("pmb_galerkin", g, self.Ac.grid, dv.ptr(A._buf), dv.ptr(self.Ac._buf), dv.stream())
+        self.Ac.invalidate()
+        if self.inner_level is None:
+            self.inner_level = SolverDenseInverse()
+        self.inner_level.update(self.Ac)
+
+    def solve(self, rhs, x0=None, trans="N"):
+        _check_trans(trans)
+        b = dv.to_device(rhs).reshape(-1)
+        A, D, w = self.A, self.smoother.D, float(self.smoother.w)
+        n = A.shape[0]
+        st = dv.stream()
+        u, u2, t, rc = self._buf["u"], self._buf["u2"], self._buf["t"], self._buf["rc"]
+        # pre-smoothing
+        if x0 is None:
+            _lib.call("pmb_smooth0", n, w, dv.ptr(b), dv.ptr(D), dv.ptr(u), st)
+        else:
+            A.apply(_lib.JACOBI, dv.to_device(x0).reshape(-1), u, b=b, diag=D, w=w)
+        for _ in range(self.smooth_steps - 1):
+            A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=w)
+            u, u2 = u2, u
+        # coarse-grid correction
+        A.apply(_lib.RESIDUAL, u, t, b=b)
+        _lib.call("pmb_restrict", A.grid, self.Ac.grid, dv.ptr(t), dv.ptr(rc), st)
+        uc = self.inner_level.solve(rc)
+        _lib.call("pmb_prolong_add", A.grid, self.Ac.grid, dv.ptr(uc), dv.ptr(u), st)
+        # post-smoothing
+        for _ in range(self.smooth_steps):
+            A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=w)
+            u, u2 = u2, u
+        self._buf["u"], self._buf["u2"] = u, u2  # the result lives in an internal buffer until the next solve()
+        return dv.like_input(u, rhs)
+
+
+def auto_multigrid(domain, min_size=8):
+    """The level chain of examples/topology_optimization/ex_compliance_multigrid.py:107-121: coarsen while every
+    coarse dimension stays even and >= ``min_size``.  Returns the list of levels, finest first."""
+    mgs = [GeometricMultigrid(domain)]
+    while True:
+        size = mgs[-1].sub_domain.size
+        if any(n % 2 != 0 for n in size) or any(size < min_size):
+            break
+        mgs.append(GeometricMultigrid(mgs[-1].sub_domain))
+        mgs[-2].inner_level = mgs[-1]
+    return mgs
+
+
+class CG(LinearSolver):
+    """Preconditioned conjugate gradients, the reference's variant (pymoto/solvers/iterative.py:295-403):
+    ``p0 = z/|z|``, ``alpha = (p.q)^-1 p.r``, ``beta = -(p.q)^-1 q.z``, explicit residual every ``restart``
+    iterations (including the first), stop on ``|r|/|b| <= tol``.  One right-hand side at a time."""
+
+    def __init__(self, A=None, preconditioner: Preconditioner = None, tol: float = 1e-7, maxit: int = 10000,
+                 restart: int = 50, verbosity: int = 0):
+        self.preconditioner = Preconditioner() if preconditioner is None else preconditioner
+        self.A = None
+        self.tol = tol
+        self.maxit = maxit
+        self.restart = restart
+        self.verbosity = verbosity
+        self.iterations = 0  # products q = A p of the last solve (the reference prints this minus one)
+        self.last_residual = None
+        super().__init__(A)
+
+    def update(self, A):
+        _check_matrix(A, "CG")
+        tstart = time.perf_counter()
+        self.A = A
+        self.preconditioner.update(A)
+        if self.verbosity >= 1:
+            torch.cuda.synchronize()
+            print(f"CG Preconditioner set up in {np.round(time.perf_counter() - tstart, 3)}s")
+
+    def solve(self, rhs, x0=None, trans="N"):
+        _check_trans(trans)
+        bd = dv.to_device(rhs)
+        if bd.ndim == 2:
+            cols = []
+            for i in range(bd.shape[1]):
+                x0i = None if x0 is None else dv.to_device(x0)[:, i].contiguous()
+                cols.append(self._solve1(bd[:, i].contiguous(), x0i).clone())
+            return dv.like_input(torch.stack(cols, dim=1), rhs)
+        return dv.like_input(self._solve1(bd.reshape(-1), None if x0 is None else dv.to_device(x0).reshape(-1)), rhs)
+
+    def _solve1(self, b, x0):
+        A, M = self.A, self.preconditioner
+        n = b.numel()
+        tstart = time.perf_counter()
+        x = dv.zeros(n) if x0 is None else x0.clone()
+        r, q, p = dv.empty(n), dv.empty(n), dv.empty(n)
+        ws = dv.workspace()
+        st = dv.stream()
+
+        A.apply(_lib.RESIDUAL, x, r, b=b)
+        d = dv.dots([(r, r), (b, b)]).cpu().numpy()
+        bnorm = np.sqrt(d[1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tval = np.sqrt(d[0]) / bnorm
+        self.iterations, self.last_residual = 0, tval
+        if self.verbosity >= 2:
+            print(f"CG Initial (max) residual = {tval}")
+        if tval <= self.tol:
+            if self.verbosity >= 1:
+                print(f"CG Converged in 0 iterations and {np.round(time.perf_counter() - tstart, 3)}s, "
+                      f"with final (max) residual {tval}")
+            return x
+
+        z = M.solve(r, trans="N")
+        zz = dv.dots([(z, z)])
+        dv.lincomb(p, _lib.coef(1.0, den=dv.scalar_ptr(zz), sqrt_den=True), z)  # p = z/|z|
+        d3 = dv.empty(3)   # [p.q, p.r, q.r]
+        rr = dv.empty(1)
+        i = 0
+        for i in range(self.maxit):
+            A.apply(_lib.SPMV, p, q, dotv=r, dot_out=d3)
+            pq, pr = dv.scalar_ptr(d3, 0), dv.scalar_ptr(d3, 1)
+            if i % self.restart == 0:  # explicit residual
+                _lib.call("pmb_cg_xr_update", n, dv.ptr(x), None, dv.ptr(p), None, pr, pq, None, None, st)
+                A.apply(_lib.RESIDUAL, x, r, b=b)
+                rr = dv.dots([(r, r)])
+            else:
+                _lib.call("pmb_cg_xr_update", n, dv.ptr(x), dv.ptr(r), dv.ptr(p), dv.ptr(q), pr, pq, dv.ptr(rr),
+                          dv.ptr(ws.red), st)
+            tval = np.sqrt(float(rr[0].item())) / bnorm  # the only host sync of the iteration
+            self.iterations, self.last_residual = i + 1, tval
+            if self.verbosity >= 2:
+                print(f"CG i = {i}, residuals = {tval}")
+            if tval <= self.tol:
+                break
+            z = M.solve(r, trans="N")
+            qz = dv.dots([(q, z)])
+            # p = z + beta p, beta = -(q.z)/(p.q)
+            dv.lincomb(p, 1.0, z, _lib.coef(-1.0, num=dv.scalar_ptr(qz), den=pq), p)
+
+        if tval > self.tol:
+            warnings.warn(f"CG Maximum iterations ({self.maxit}) reached, with final residuals {tval}")
+        elif self.verbosity >= 1:
+            print(f"CG Converged in {i} iterations and {np.round(time.perf_counter() - tstart, 3)}s, "
+                  f"with final (max) residual {tval}")
+        return x
+
+
+class LDAWrapper(LinearSolver):
+    """Linear-dependency-aware solver (pymoto/solvers/solvers.py:99-306) for real symmetric DeviceCSR matrices.
+
+    Dirichlet dofs (rows whose only non-zero is the diagonal, solvers.py:88-96) are solved as ``f/diag``; the
+    right-hand side is projected on the stored normalised ``(x, b = A x)`` pairs (modified Gram-Schmidt); only
+    if the residual exceeds ``tol`` is the inner solver called on the remainder and the new pair stored.  The
+    database is cleared on every ``update``.  For a symmetric matrix the adjoint solve (``trans="T"``) uses the
+    same database, which makes the compliance adjoint cost one SpMV and no CG iteration.
+    """
+
+    def __init__(self, solver: LinearSolver, tol=1e-7, A=None, symmetric=None, hermitian=None):
+        self.solver = solver
+        self.tol = tol
+        self.x_stored, self.b_stored = [], []
+        self.A = None
+        self._did_solve = False
+        self._last_rtol = 0.0
+        self.symmetric, self.hermitian = True, True
+        self.complex = False
+        super().__init__(A)
+
+    def update(self, A, skip_inner_update: bool = False):
+        _check_matrix(A, "LDAWrapper")
+        self.A = A
+        diag, nnz_off = A.rowstats()
+        n = A.shape[0]
+        self._diag = diag
+        self._mask = dv.empty(n, torch.uint8)
+        _lib.call("pmb_diag_mask", n, dv.ptr(diag), dv.ptr(nnz_off), dv.ptr(self._mask), dv.stream())
+        self.x_stored.clear()
+        self.b_stored.clear()
+        if not skip_inner_update:
+            self.solver.update(A)
+
+    @property
+    def diagonal_idx(self):
+        return torch.nonzero(self._mask).flatten().cpu().numpy()
+
+    def _solve1(self, rhs, x0):
+        A, n, st = self.A, self.A.shape[0], dv.stream()
+        sol, rhs_loc = dv.empty(n), dv.empty(n)
+        _lib.call("pmb_bc_split", n, dv.ptr(self._mask), dv.ptr(rhs), dv.ptr(self._diag), dv.ptr(sol), dv.ptr(rhs_loc), st)
+        # project on the database (stored vectors are zero at the Dirichlet dofs)
+        for x, b in zip(self.x_stored, self.b_stored):
+            d = dv.dots([(rhs_loc, b), (b, b)])
+            num, den = dv.scalar_ptr(d, 0), dv.scalar_ptr(d, 1)
+            dv.lincomb(rhs_loc, 1.0, rhs_loc, _lib.coef(-1.0, num=num, den=den), b)
+            dv.lincomb(sol, 1.0, sol, _lib.coef(1.0, num=num, den=den), x)
+        self._last_rtol = self.residual(A, sol, rhs)
+        self._did_solve = self._last_rtol > self.tol
+        if self._did_solve:
+            x0_loc = None
+            if x0 is not None:
+                x0_loc = dv.empty(n)
+                _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(x0), dv.ptr(x0_loc), st)
+                for x in self.x_stored:
+                    d = dv.dots([(x0_loc, x), (x, x)])
+                    dv.lincomb(x0_loc, 1.0, x0_loc, _lib.coef(-1.0, num=dv.scalar_ptr(d, 0), den=dv.scalar_ptr(d, 1)), x)
+            xnew = self.solver.solve(rhs_loc, x0=x0_loc, trans="N")
+            xadd = dv.empty(n)
+            _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(xnew), dv.ptr(xadd), st)
+            dv.lincomb(sol, 1.0, sol, 1.0, xadd)
+            badd = dv.empty(n)
+            A.apply(_lib.SPMV, xnew, badd)
+            _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(badd), dv.ptr(badd), st)
+            for x, b in zip(self.x_stored, self.b_stored):
+                d = dv.dots([(badd, b), (b, b)])
+                num, den = dv.scalar_ptr(d, 0), dv.scalar_ptr(d, 1)
+                dv.lincomb(badd, 1.0, badd, _lib.coef(-1.0, num=num, den=den), b)
+                dv.lincomb(xadd, 1.0, xadd, _lib.coef(-1.0, num=num, den=den), x)
+            bb = dv.dots([(badd, badd)])
+            bnrm2 = float(bb[0].item())
+            if np.isfinite(bnrm2) and bnrm2 != 0:
+                inv = _lib.coef(1.0, den=dv.scalar_ptr(bb), sqrt_den=True)
+                dv.lincomb(badd, inv, badd)
+                dv.lincomb(xadd, inv, xadd)
+                self.x_stored.append(xadd)
+                self.b_stored.append(badd)
+        return sol
+
+    def solve(self, rhs, x0=None, trans="N"):
+        trans = trans.upper()
+        _check_trans(trans)
+        bd = dv.to_device(rhs)
+        x0d = None if x0 is None else dv.to_device(x0)
+        if bd.ndim == 2:
+            cols = [self._solve1(bd[:, i].contiguous(), None if x0d is None else x0d[:, i].contiguous())
+                    for i in range(bd.shape[1])]
+            return dv.like_input(torch.stack(cols, dim=1), rhs)
+        return dv.like_input(self._solve1(bd.reshape(-1), None if x0d is None else x0d.reshape(-1)), rhs)
