@@ -17,9 +17,10 @@ from .dyad import DeviceDyad
 from .assembly import AssembleGeneral, AssembleStiffness, AssemblePoisson
 from .filter import DensityFilter, Filter
 from .linalg import LinSolve
+from .glue import SIMP, Compliance
 from . import solvers
 from ._lib import PmbError
 
 __all__ = ["Signal", "Module", "Network", "VoxelDomain", "DomainDefinition", "DeviceCSR", "DeviceDyad",
-           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "LinSolve", "solvers",
+           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "LinSolve", "SIMP", "Compliance", "solvers",
            "PmbError", "HAVE_PYMOTO"]

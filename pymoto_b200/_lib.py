@@ -74,7 +74,17 @@ SIGNATURES = {
 SPMV, RESIDUAL, JACOBI = 0, 1, 2
 
 _lib = None
-launch_count = 0  # number of libpmb kernel-launching calls made (bench.py reports it)
+launch_count = 0  # CUDA kernels launched by libpmb through this binding (bench.py reports it as gpu_launches)
+call_stats = {}   # (entry point, detail) -> number of calls; detail = (nx, mode) for pmb_spmv
+
+
+def _kernels_launched(name, args):
+    """How many kernels one C-ABI call launches (see the .cu sources)."""
+    if name == "pmb_spmv":
+        return 2 if args[9] is not None else 1  # + reduce_triples_kernel when the fused dots are requested
+    if name == "pmb_dense_invert":
+        return 2 * int(args[0])  # one copy + one update kernel per Gauss-Jordan step
+    return 1
 
 
 def load():
@@ -99,7 +109,9 @@ def call(name, *args):
     global launch_count
     lib = load()
     rc = getattr(lib, name)(*args)
-    launch_count += 1
+    launch_count += _kernels_launched(name, args)
+    key = (name, (args[0].nx, args[1])) if name == "pmb_spmv" else (name, None)
+    call_stats[key] = call_stats.get(key, 0) + 1
     if rc != 0:
         raise PmbError(f"{name} failed: {lib.pmb_last_error().decode()}")
 
