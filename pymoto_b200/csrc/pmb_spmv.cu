@@ -5,29 +5,38 @@
 // plus DampedJacobi (iterative.py:38-47) and get_diagonal_indices (solvers.py:88-96).
 //
 // Layout: the matrix is the reference's own CSR `data` array.  On a structured grid all rows of T consecutive
-// nodes are ONE contiguous run of doubles, so a CTA streams that run with 128-bit loads into shared memory
-// (fully coalesced, no index traffic: indptr/indices are closed-form), then PARTS threads per node multiply
-// their part of the node's NDOF x (27*NDOF) block against x gathered through L1.
+// nodes are ONE contiguous run of doubles and indptr/indices are closed-form, so no index is ever read.
+//
+// Kernel: persistent CTAs (2 per SM) walk the tiles round-robin.  One elected thread streams each tile's run into
+// a 3-stage shared-memory ring with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes, L2
+// evict-first for matrices larger than L2), so loads of tiles t+1, t+2 are in flight while tile t is multiplied.
+// PARTS threads per node each take one line of the 27-point stencil (<= 3 neighbour nodes x NDOF columns for all
+// NDOF rows of the node), x is gathered through L1, the PARTS partial sums of a row are combined in fixed order
+// through shared memory and the epilogue (residual / Jacobi update / fused dot products) is applied per row.
+#include <cstdint>
 #include "pmb_common.cuh"
 
 enum { MODE_SPMV = PMB_SPMV, MODE_RESID = PMB_RESIDUAL, MODE_JACOBI = PMB_JACOBI, MODE_ROWSTATS = 3 };
 
-// T nodes per CTA, PARTS threads per node; NT = threads per CTA rounded up to whole warps (the padding threads
-// only help with the staging loads); SMEM_DOUBLES = largest staged run (+2 for the 16-byte alignment slack)
-template <int NDOF, int T_, int PARTS_>
+// T nodes per tile, PARTS threads per node, STAGES ring slots; NT = threads per CTA rounded up to whole warps;
+// TILE_DOUBLES = largest staged run (+2 for the 16-byte alignment slack), itself kept a multiple of 2.
+template <int NDOF, int T_, int PARTS_, int STAGES_>
 struct TileCfgBase {
-  static constexpr int T = T_, PARTS = PARTS_;
+  static constexpr int T = T_, PARTS = PARTS_, STAGES = STAGES_;
   static constexpr int NT = (T_ * PARTS_ + 31) / 32 * 32;
-  static constexpr int SMEM_DOUBLES = T_ * NDOF * NDOF * 27 + 2;
+  static constexpr int TILE_DOUBLES = (T_ * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * TILE_DOUBLES * STAGES_;
 };
 template <int NDOF>
 struct TileCfg;
 template <>
-struct TileCfg<3> : TileCfgBase<3, 16, 9> {};
+struct TileCfg<3> : TileCfgBase<3, 16, 9, 3> {};
 template <>
-struct TileCfg<2> : TileCfgBase<2, 48, 3> {};
+struct TileCfg<2> : TileCfgBase<2, 48, 3, 2> {};
 template <>
-struct TileCfg<1> : TileCfgBase<1, 96, 3> {};
+struct TileCfg<1> : TileCfgBase<1, 96, 3, 3> {};
+
+static constexpr int CTAS_PER_SM = 2;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -35,122 +44,223 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar, bool stream_hint) {
+  if (stream_hint) {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+
+// Tiles never straddle an x-row of nodes: tile = (row (j,k), i0 .. i0+T), so (cy, cz) are uniform per tile and a
+// node's offset inside the tile is closed-form in i alone.
+struct TileGeom {
+  int i0, ni, j, k, cy, cz, jlo, klo;
+  long long e0;  // entry offset (slab-relative) of the tile's first entry
+  long long e1;  // one past its last entry
+};
+
+template <int NDOF, int T>
+__device__ __forceinline__ TileGeom tile_geom(const Geo& g, int tile, int tiles_per_row) {
+  TileGeom t;
+  const int row = tile / tiles_per_row;
+  const int ti = tile - row * tiles_per_row;
+  const int kl = row / g.NY;
+  t.j = row - kl * g.NY;
+  t.k = kl + g.kz0;
+  t.i0 = ti * T;
+  t.ni = min(T, g.NX - t.i0);
+  t.cy = cnt1(t.j, g.NY);
+  t.cz = cnt1(t.k, g.NZ);
+  t.jlo = max(t.j - 1, 0);
+  t.klo = max(t.k - 1, 0);
+  const long long rowbase = pre1(t.k, g.NZ) * g.Sy * g.Sx + (long long)t.cz * (pre1(t.j, g.NY) * g.Sx) - g.bo0;
+  const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
+  t.e0 = (long long)(NDOF * NDOF) * rowbase + per * pre1(t.i0, g.NX);
+  t.e1 = (long long)(NDOF * NDOF) * rowbase + per * pre1(t.i0 + t.ni, g.NX);
+  return t;
+}
+
 template <int NDOF, int MODE>
-__global__ void __launch_bounds__(TileCfg<NDOF>::NT)
-    tile_kernel(Geo g, const double* __restrict__ A, const double* __restrict__ x, const double* __restrict__ b,
-                const double* __restrict__ diag, double w, double* __restrict__ y, const double* __restrict__ dotv,
-                double* __restrict__ partials, int* __restrict__ nnz_out) {
-  constexpr int T = TileCfg<NDOF>::T, PARTS = TileCfg<NDOF>::PARTS, NT = TileCfg<NDOF>::NT;
-  extern __shared__ double2 smem2[];
-  double* sA = reinterpret_cast<double*>(smem2);
-  __shared__ double red[PARTS][T * NDOF];
-  __shared__ double red2[MODE == MODE_ROWSTATS ? PARTS : 1][MODE == MODE_ROWSTATS ? T * NDOF : 1];
+__global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)
+    tile_kernel(Geo g, int ntiles, int tiles_per_row, int stream_hint, const double* __restrict__ A,
+                const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ diag, double w,
+                double* __restrict__ y, const double* __restrict__ dotv, double* __restrict__ partials,
+                int* __restrict__ nnz_out) {
+  using Cfg = TileCfg<NDOF>;
+  constexpr int T = Cfg::T, PARTS = Cfg::PARTS, NT = Cfg::NT, STAGES = Cfg::STAGES, TD = Cfg::TILE_DOUBLES;
+  constexpr int LINES = 9 / PARTS;  // stencil lines (jj, kk) per thread: 1 (PARTS = 9) or 3 (PARTS = 3: one kk plane)
+  extern __shared__ __align__(128) double sTiles[];  // STAGES x TD doubles
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ double red[2][PARTS][T * NDOF];
+  __shared__ double red2[MODE == MODE_ROWSTATS ? 2 : 1][MODE == MODE_ROWSTATS ? PARTS : 1][MODE == MODE_ROWSTATS ? T * NDOF : 1];
   __shared__ double wred[3][NT / 32];
 
   const int tid = threadIdx.x;
-  const long long n0 = (long long)blockIdx.x * T;
-  const long long nEnd = min(n0 + T, g.nOwned);
-  const long long e0 = node_entry_offset(g, n0);
-  const long long e1 = node_entry_offset(g, nEnd);
-  const long long lo = e0 & ~1LL;
-  const long long hi = (e1 + 1) & ~1LL;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles blockIdx.x + i*gridDim.x
 
-  // ---- stage the contiguous run of matrix values (streaming, 128-bit, evict-first)
-  {
-    const double2* g2 = reinterpret_cast<const double2*>(A + lo);
-    const int nvec = (int)((hi - lo) >> 1);
-    for (int v = tid; v < nvec; v += NT) smem2[v] = __ldcs(g2 + v);
+  // producer: issue the TMA bulk copy of this CTA's i-th tile into ring slot i % STAGES
+  auto issue = [&](int i) {
+    const int s = i % STAGES;
+    const TileGeom t = tile_geom<NDOF, T>(g, (int)blockIdx.x + i * (int)gridDim.x, tiles_per_row);
+    const long long lo = t.e0 & ~1LL;
+    const long long hi = (t.e1 + 1) & ~1LL;
+    const unsigned bytes = (unsigned)((hi - lo) * sizeof(double));
+    mbar_expect_tx(&full_bar[s], bytes);
+    tma_load_1d(sTiles + (size_t)s * TD, A + lo, bytes, &full_bar[s], stream_hint != 0);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < STAGES && i < my_tiles; ++i) issue(i);
   }
   __syncthreads();
 
   const int gI = tid % T, q = tid / T;
-  const long long ln = n0 + gI;
-  double acc[NDOF], acc2[NDOF];
-#pragma unroll
-  for (int d = 0; d < NDOF; ++d) acc[d] = 0.0, acc2[d] = 0.0;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;  // fused dot-product partials, accumulated over this CTA's tiles
 
-  if (ln < nEnd && q < PARTS) {
-    int i, j, k;
-    node_ijk(g, ln, i, j, k);
-    const int cx = cnt1(i, g.NX), cy = cnt1(j, g.NY), cz = cnt1(k, g.NZ);
-    const int ilo = max(i - 1, 0), jlo = max(j - 1, 0), klo = max(k - 1, 0);
-    const int L = cx * cy * cz * NDOF;
-    const double* rowp = sA + ((long long)(NDOF * NDOF) * (block_offset(g, i, j, k) - g.bo0) - lo);
-    int kk0, kk1, jj0, jj1;
-    if (PARTS == 9) {
-      kk0 = q / 3; kk1 = kk0 + 1; jj0 = q % 3; jj1 = jj0 + 1;
-    } else {
-      kk0 = q; kk1 = q + 1; jj0 = 0; jj1 = 3;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int s = it % STAGES;
+    const TileGeom t = tile_geom<NDOF, T>(g, (int)blockIdx.x + it * (int)gridDim.x, tiles_per_row);
+    const long long lnode0 = ((long long)(t.k - g.kz0) * g.NY + t.j) * g.NX + t.i0;  // slab-local index of the tile's first node
+    const int i = t.i0 + gI;
+    const bool active = (gI < t.ni) && (q < PARTS);
+
+    // ---- everything that does not depend on the matrix values is issued before waiting for the tile:
+    //      the x gathers of this thread's stencil line(s) and the epilogue operands of this thread's row
+    const int cx = cnt1(i, g.NX), ilo = max(i - 1, 0);
+    double xv[LINES][3][NDOF];
+    bool lvalid[LINES];
+#pragma unroll
+    for (int l = 0; l < LINES; ++l) {
+      const int kkI = (PARTS == 9) ? q / 3 : q;
+      const int jjI = (PARTS == 9) ? q % 3 : l;
+      lvalid[l] = active && kkI < t.cz && jjI < t.cy;
+      const long long c0 = ((long long)(t.klo + kkI - g.kz0) * g.NY + (t.jlo + jjI)) * g.NX + ilo;
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int cd = 0; cd < NDOF; ++cd)
+          xv[l][n][cd] = (MODE != MODE_ROWSTATS && lvalid[l] && n < cx) ? __ldg(x + (c0 + n) * NDOF + cd) : 0.0;
     }
-    kk1 = min(kk1, cz);
-    jj1 = min(jj1, cy);
-    for (int kkI = kk0; kkI < kk1; ++kkI) {
-      for (int jjI = jj0; jjI < jj1; ++jjI) {
-        const int nbr0 = (kkI * cy + jjI) * cx;
-        const long long c0 = ((long long)(klo + kkI - g.kz0) * g.NY + (jlo + jjI)) * g.NX + ilo;
-        for (int iiI = 0; iiI < cx; ++iiI) {
-          const double* ap = rowp + (nbr0 + iiI) * NDOF;
-          if (MODE == MODE_ROWSTATS) {
-            const bool self = (c0 + iiI) == ln;
+    const bool erow = (tid < T * NDOF) && (tid / NDOF < t.ni);
+    const long long r = (lnode0 * NDOF) + tid;  // global (slab-local) row of the epilogue thread
+    double xr = 0.0, br = 0.0, dr = 1.0, dvr = 0.0;
+    if (MODE != MODE_ROWSTATS && erow) {
+      if (MODE == MODE_JACOBI || partials) xr = x[r];
+      if (MODE != MODE_SPMV) br = b[r];
+      if (MODE == MODE_JACOBI) dr = diag[r];
+      if (partials && dotv) dvr = dotv[r];
+    }
+
+    mbar_wait(&full_bar[s], (unsigned)((it / STAGES) & 1));
+
+    double acc[NDOF], acc2[NDOF];
 #pragma unroll
-            for (int d = 0; d < NDOF; ++d)
+    for (int d = 0; d < NDOF; ++d) acc[d] = 0.0, acc2[d] = 0.0;
+    {
+      const int L = cx * t.cy * t.cz * NDOF;
+      const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
+      const double* rowp = sTiles + (size_t)s * TD + ((t.e0 - (t.e0 & ~1LL)) + per * (pre1(i, g.NX) - pre1(t.i0, g.NX)));
 #pragma unroll
-              for (int cd = 0; cd < NDOF; ++cd) {
-                double a = ap[d * L + cd];
-                if (self && cd == d) acc[d] = a;
-                else acc2[d] += (a != 0.0) ? 1.0 : 0.0;
-              }
-          } else {
-            double xv[NDOF];
-            const double* xp = x + (c0 + iiI) * NDOF;
+      for (int l = 0; l < LINES; ++l) {
+        if (!lvalid[l]) continue;
+        const int kkI = (PARTS == 9) ? q / 3 : q;
+        const int jjI = (PARTS == 9) ? q % 3 : l;
+        const double* lp = rowp + (kkI * t.cy + jjI) * cx * NDOF;
 #pragma unroll
-            for (int cd = 0; cd < NDOF; ++cd) xv[cd] = __ldg(xp + cd);
+        for (int n = 0; n < 3; ++n) {
+          if (n < cx) {
+            const double* ap = lp + n * NDOF;
+            if (MODE == MODE_ROWSTATS) {
+              const bool self = (t.klo + kkI == t.k) && (t.jlo + jjI == t.j) && (ilo + n == i);
 #pragma unroll
-            for (int d = 0; d < NDOF; ++d)
+              for (int d = 0; d < NDOF; ++d)
 #pragma unroll
-              for (int cd = 0; cd < NDOF; ++cd) acc[d] = fma(ap[d * L + cd], xv[cd], acc[d]);
+                for (int cd = 0; cd < NDOF; ++cd) {
+                  const double a = ap[d * L + cd];
+                  if (self && cd == d) acc[d] = a;
+                  else acc2[d] += (a != 0.0) ? 1.0 : 0.0;
+                }
+            } else {
+#pragma unroll
+              for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+                for (int cd = 0; cd < NDOF; ++cd) acc[d] = fma(ap[d * L + cd], xv[l][n][cd], acc[d]);
+            }
           }
         }
       }
     }
-  }
-  if (q < PARTS) {
+    const int rb = it & 1;  // double-buffered combine area: the next tile's writes cannot race this tile's reads
+    if (q < PARTS) {
 #pragma unroll
-    for (int d = 0; d < NDOF; ++d) {
-      red[q][gI * NDOF + d] = acc[d];
-      if (MODE == MODE_ROWSTATS) red2[q][gI * NDOF + d] = acc2[d];
+      for (int d = 0; d < NDOF; ++d) {
+        red[rb][q][gI * NDOF + d] = acc[d];
+        if (MODE == MODE_ROWSTATS) red2[rb][q][gI * NDOF + d] = acc2[d];
+      }
     }
-  }
-  __syncthreads();
+    __syncthreads();  // every thread is done reading ring slot s
 
-  // ---- combine the PARTS partial sums of each row in fixed order, then the per-row epilogue
-  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-  if (tid < T * NDOF) {
-    const long long node = n0 + tid / NDOF;
-    if (node < nEnd) {
-      const long long r = n0 * NDOF + tid;
+    if (tid == 0 && it + STAGES < my_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before the async-proxy refill
+      issue(it + STAGES);
+    }
+
+    // ---- combine the PARTS partial sums of each row in fixed order, then the per-row epilogue
+    if (erow) {
       double ax = 0.0;
 #pragma unroll
-      for (int p = 0; p < PARTS; ++p) ax += red[p][tid];
+      for (int p = 0; p < PARTS; ++p) ax += red[rb][p][tid];
       if (MODE == MODE_ROWSTATS) {
         double c = 0.0;
 #pragma unroll
-        for (int p = 0; p < PARTS; ++p) c += red2[p][tid];
+        for (int p = 0; p < PARTS; ++p) c += red2[rb][p][tid];
         if (y) y[r] = ax;
         if (nnz_out) nnz_out[r] = (int)c;
       } else {
         double out;
         if (MODE == MODE_SPMV) out = ax;
-        else if (MODE == MODE_RESID) out = b[r] - ax;
-        else out = x[r] + w * ((b[r] - ax) / diag[r]);
+        else if (MODE == MODE_RESID) out = br - ax;
+        else out = xr + w * ((br - ax) / dr);
         y[r] = out;
         if (partials) {
-          d0 = out * x[r];
-          if (dotv) d1 = x[r] * dotv[r], d2 = out * dotv[r];
+          d0 = fma(out, xr, d0);
+          d1 = fma(xr, dvr, d1);
+          d2 = fma(out, dvr, d2);
         }
       }
     }
   }
+
   if (MODE != MODE_ROWSTATS && partials) {
     d0 = warp_sum(d0);
     d1 = warp_sum(d1);
@@ -186,32 +296,52 @@ __global__ void __launch_bounds__(1024) reduce_triples_kernel(const double* __re
   }
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int NDOF>
-static long long tile_blocks(const Geo& g) { return (g.nOwned + TileCfg<NDOF>::T - 1) / TileCfg<NDOF>::T; }
+static int tiles_per_row(const Geo& g) { return (g.NX + TileCfg<NDOF>::T - 1) / TileCfg<NDOF>::T; }
+template <int NDOF>
+static long long tile_count(const Geo& g) { return (long long)tiles_per_row<NDOF>(g) * g.NY * g.nzl; }
+
+static int grid_for(long long ntiles) {
+  long long cap = (long long)sm_count() * CTAS_PER_SM;
+  return (int)(ntiles < cap ? ntiles : cap);
+}
 
 extern "C" long long pmb_spmv_ws_doubles(const pmb_grid* p) {
   if (validate_grid(p, "pmb_spmv_ws_doubles")) return -1;
-  Geo g = make_geo(p);
-  long long nb = g.ndof == 3 ? tile_blocks<3>(g) : g.ndof == 2 ? tile_blocks<2>(g) : tile_blocks<1>(g);
-  return 3 * nb;
+  return 3LL * sm_count() * CTAS_PER_SM;
 }
 
 template <int NDOF, int MODE>
 static int launch_tile(const Geo& g, const double* A, const double* x, const double* b, const double* diag, double w,
                        double* y, const double* dotv, double* dot_out, double* ws, int* nnz_out, cudaStream_t st) {
-  constexpr int NT = TileCfg<NDOF>::NT;
-  const size_t smem = sizeof(double) * TileCfg<NDOF>::SMEM_DOUBLES;
+  using Cfg = TileCfg<NDOF>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel<NDOF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel<NDOF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return pmb_set_error("tile_kernel attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  long long nb = tile_blocks<NDOF>(g);
-  tile_kernel<NDOF, MODE><<<(unsigned)nb, NT, smem, st>>>(g, A, x, b, diag, w, y, dotv, dot_out ? ws : nullptr, nnz_out);
+  const long long ntiles = tile_count<NDOF>(g);
+  PMB_REQUIRE(ntiles < 2147483647LL, "pmb_spmv: too many tiles");
+  const int grid = grid_for(ntiles);
+  // matrices that do not fit in L2 anyway are streamed evict-first so the x / b / y vectors keep their lines
+  const long long nnz_bytes = 8LL * NDOF * NDOF * (pre1(g.kz0 + g.nzl, g.NZ) * g.Sy * g.Sx - g.bo0);
+  const int stream_hint = nnz_bytes > (96LL << 20);
+  tile_kernel<NDOF, MODE><<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(g, (int)ntiles, tiles_per_row<NDOF>(g), stream_hint, A, x, b, diag, w, y, dotv,
+                                                                  dot_out ? ws : nullptr, nnz_out);
   PMB_CHECK_LAUNCH("pmb_spmv");
   if (dot_out) {
-    reduce_triples_kernel<<<1, 1024, 0, st>>>(ws, nb, dot_out);
+    reduce_triples_kernel<<<1, 1024, 0, st>>>(ws, grid, dot_out);
     PMB_CHECK_LAUNCH("pmb_spmv(reduce)");
   }
   return 0;
