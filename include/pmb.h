@@ -99,8 +99,9 @@ int pmb_smooth0(long long n, double w, const double* r, const double* diag, doub
 int pmb_restrict(const pmb_grid* gf, const pmb_grid* gc, const double* rf, double* rc, void* stream);
 /* K5: uf += R uc */
 int pmb_prolong_add(const pmb_grid* gf, const pmb_grid* gc, const double* uc, double* uf, void* stream);
-/* K6: Ac = R^T A R in the coarse grid's own stencil-CSR layout */
-int pmb_galerkin(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* Ac, void* stream);
+/* K6: Ac = R^T A R in the coarse grid's own stencil-CSR layout; work holds pmb_galerkin_ws_doubles(gf) doubles */
+int pmb_galerkin(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* Ac, double* work, void* stream);
+long long pmb_galerkin_ws_doubles(const pmb_grid* gf);
 
 /* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (Gauss-Jordan without
  * pivoting, valid for SPD); scratch holds 2n doubles; info (device int) is set non-zero on a non-positive pivot. */

@@ -55,7 +55,8 @@ SIGNATURES = {
     "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
     "pmb_restrict": (_I, [_G, _G, _P, _P, _P]),
     "pmb_prolong_add": (_I, [_G, _G, _P, _P, _P]),
-    "pmb_galerkin": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_galerkin": (_I, [_G, _G, _P, _P, _P, _P]),
+    "pmb_galerkin_ws_doubles": (_LL, [_G]),
     "pmb_densify": (_I, [_G, _P, _P, _P]),
     "pmb_dense_invert": (_I, [_I, _P, _P, _P, _P]),
     "pmb_dense_gemv": (_I, [_I, _P, _P, _P, _P]),
@@ -82,6 +83,8 @@ def _kernels_launched(name, args):
     """How many kernels one C-ABI call launches (see the .cu sources)."""
     if name == "pmb_spmv":
         return 2 if args[9] is not None else 1  # + reduce_triples_kernel when the fused dots are requested
+    if name == "pmb_galerkin":
+        return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":
         return 2 * int(args[0])  # one copy + one update kernel per Gauss-Jordan step
     return 1

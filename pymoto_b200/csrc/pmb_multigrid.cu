@@ -4,7 +4,7 @@
 // Replaces pymoto/solvers/iterative.py:178-220 (the prolongation matrix R is never formed: its trilinear
 // weights 1, 1/2, 1/4, 1/8 are closed-form), :244 (R^T r via csc_matvec), :250 (u += R u_c via csr_matvec),
 // :173 (R^T A R via two csr_matmat) and the coarsest-level splu of pymoto/solvers/sparse.py:533-550.
-#include "pmb_common.cuh"
+#include "pmb_tilestream.cuh"
 
 // ------------------------------------------------------------------------------------------------- K4
 // rc[C] = sum over the <= 27 fine nodes 2C+d of w(d) rf[fine]; ascending fine node number, separate multiply and
@@ -84,63 +84,141 @@ extern "C" int pmb_prolong_add(const pmb_grid* pf, const pmb_grid* pc, const dou
 }
 
 // ------------------------------------------------------------------------------------------------- K6
-// Ac[(C,dI),(C+D,dJ)] = sum_{i in supp(C), j in supp(C+D), j neighbour of i} w_C(i) w_{C+D}(j) Af[(i,dI),(j,dJ)]
-// One thread per coarse (node, neighbour slot) = one NDOF x NDOF block, gathered straight from the fine
-// stencil-CSR values; the result lands in the coarse grid's own stencil-CSR layout.
+// Ac = R^T A R as two streaming gather passes (no atomics, no SpGEMM, R never formed):
+//   pass 1 (columns): B[i, C] = sum_{j nbr of i, j in supp(C)} w_C(j) A[i, j]   for fine row-node i and the <= 27 coarse
+//                     nodes C around it; the fine matrix is streamed once through the same TMA tile ring as the
+//                     operator kernel and each (i, C) block is gathered from shared memory;
+//   pass 2 (rows):    Ac[I, C] = sum_{i in supp(I)} w_I(i) B[i, C], written straight into the coarse stencil-CSR layout.
+// B is stored padded: 27 coarse slots x NDOF^2 per fine node (slot = per-dimension offset C - (f >> 1) + 1).
 template <int NDOF>
-__global__ void __launch_bounds__(128) galerkin_kernel(Geo gf, Geo gc, const double* __restrict__ Af, double* __restrict__ Ac) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+struct GalCfg;
+template <>
+struct GalCfg<3> { static constexpr int T = 16, STAGES = 3; };
+template <>
+struct GalCfg<2> { static constexpr int T = 48, STAGES = 2; };
+template <>
+struct GalCfg<1> { static constexpr int T = 96, STAGES = 3; };
+static constexpr int GAL_NT = 256;
+
+template <int NDOF>
+__global__ void __launch_bounds__(GAL_NT, 2) galerkin_cols_kernel(Geo gf, Geo gc, int ntiles, int tiles_per_row, int stream_hint,
+                                                                  const double* __restrict__ Af, double* __restrict__ B) {
+  constexpr int T = GalCfg<NDOF>::T, STAGES = GalCfg<NDOF>::STAGES;
+  constexpr int TD = (T * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
+  extern __shared__ __align__(128) double sTiles[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  const int tid = threadIdx.x;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto issue = [&](int i) {
+    const int s = i % STAGES;
+    const TileGeom t = tile_geom<NDOF, T>(gf, (int)blockIdx.x + i * (int)gridDim.x, tiles_per_row);
+    const long long lo = t.e0 & ~1LL;
+    const long long hi = (t.e1 + 1) & ~1LL;
+    const unsigned bytes = (unsigned)((hi - lo) * sizeof(double));
+    mbar_expect_tx(&full_bar[s], bytes);
+    tma_load_1d(sTiles + (size_t)s * TD, Af + lo, bytes, &full_bar[s], stream_hint != 0);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < STAGES && i < my_tiles; ++i) issue(i);
+  }
+  __syncthreads();
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int s = it % STAGES;
+    const TileGeom t = tile_geom<NDOF, T>(gf, (int)blockIdx.x + it * (int)gridDim.x, tiles_per_row);
+    const long long lnode0 = ((long long)(t.k - gf.kz0) * gf.NY + t.j) * gf.NX + t.i0;
+    const double* tile = sTiles + (size_t)s * TD + (t.e0 - (t.e0 & ~1LL));
+    const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
+    mbar_wait(&full_bar[s], (unsigned)((it / STAGES) & 1));
+
+    for (int p = tid; p < t.ni * 27; p += GAL_NT) {
+      const int gI = p / 27, slot = p - gI * 27;
+      const int sk = slot / 9, sj = (slot / 3) % 3, si = slot % 3;
+      const int fi = t.i0 + gI, fj = t.j, fk = t.k;
+      const int Ci = (fi >> 1) + si - 1, Cj = (fj >> 1) + sj - 1, Ck = (fk >> 1) + sk - 1;
+      const bool valid = ((fi & 1) == 0 || si >= 1) && ((fj & 1) == 0 || sj >= 1) && ((fk & 1) == 0 || sk >= 1) && Ci >= 0 &&
+                         Ci < gc.NX && Cj >= 0 && Cj < gc.NY && Ck >= 0 && Ck < gc.NZ;
+      if (!valid) continue;
+      const int cx = cnt1(fi, gf.NX), ilo = max(fi - 1, 0);
+      const int L = cx * t.cy * t.cz * NDOF;
+      const double* nodep = tile + per * (pre1(fi, gf.NX) - pre1(t.i0, gf.NX));
+      double acc[NDOF][NDOF];
+#pragma unroll
+      for (int a = 0; a < NDOF; ++a)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) acc[a][c] = 0.0;
+      for (int pk = max(fk - 1, 0); pk <= min(fk + 1, gf.NZ - 1); ++pk) {
+        const int tz = pk - 2 * Ck;
+        if (tz < -1 || tz > 1) continue;
+        for (int pj = max(fj - 1, 0); pj <= min(fj + 1, gf.NY - 1); ++pj) {
+          const int ty = pj - 2 * Cj;
+          if (ty < -1 || ty > 1) continue;
+          const double wzy = (tz ? 0.5 : 1.0) * (ty ? 0.5 : 1.0);
+          for (int pi = ilo; pi <= min(fi + 1, gf.NX - 1); ++pi) {
+            const int tx = pi - 2 * Ci;
+            if (tx < -1 || tx > 1) continue;
+            const double w = wzy * (tx ? 0.5 : 1.0);
+            const int nbr = ((pk - t.klo) * t.cy + (pj - t.jlo)) * cx + (pi - ilo);
+            const double* ap = nodep + nbr * NDOF;
+#pragma unroll
+            for (int a = 0; a < NDOF; ++a)
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) acc[a][c] = fma(w, ap[a * L + c], acc[a][c]);
+          }
+        }
+      }
+      double* bp = B + ((lnode0 + gI) * 27 + slot) * (NDOF * NDOF);
+#pragma unroll
+      for (int a = 0; a < NDOF; ++a)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) bp[a * NDOF + c] = acc[a][c];
+    }
+    __syncthreads();
+    if (tid == 0 && it + STAGES < my_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(it + STAGES);
+    }
+  }
+}
+
+// pass 2: one thread per coarse (node, neighbour slot) = one NDOF x NDOF block
+template <int NDOF>
+__global__ void __launch_bounds__(128) galerkin_rows_kernel(Geo gf, Geo gc, const double* __restrict__ B, double* __restrict__ Ac) {
+  long long tg = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long nslots = gc.nOwned * 27;
-  if (t >= nslots) return;
-  int s = (int)(t % 27);
-  long long lc = t / 27;
+  if (tg >= nslots) return;
+  int s = (int)(tg % 27);
+  long long lc = tg / 27;
   int I, J, K;
   node_ijk(gc, lc, I, J, K);
   const int Dk = s / 9 - 1, Dj = (s / 3) % 3 - 1, Di = s % 3 - 1;
   const int Ci = I + Di, Cj = J + Dj, Ck = K + Dk;
   if (Ci < 0 || Ci >= gc.NX || Cj < 0 || Cj >= gc.NY || Ck < 0 || Ck >= gc.NZ) return;
-
   double acc[NDOF][NDOF];
 #pragma unroll
   for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-    for (int b = 0; b < NDOF; ++b) acc[a][b] = 0.0;
-
+    for (int c = 0; c < NDOF; ++c) acc[a][c] = 0.0;
   for (int dz = -1; dz <= 1; ++dz) {
-    const int fk = 2 * K + dz;
-    if (fk < 0 || fk >= gf.NZ) continue;
-    const int czf = cnt1(fk, gf.NZ), klo = max(fk - 1, 0);
-    for (int ez = -1; ez <= 1; ++ez) {
-      const int pk = fk + ez, tz = pk - 2 * Ck;
-      if (pk < 0 || pk >= gf.NZ || tz < -1 || tz > 1) continue;
-      const double wz = (dz ? 0.5 : 1.0) * (tz ? 0.5 : 1.0);
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int fj = 2 * J + dy;
-        if (fj < 0 || fj >= gf.NY) continue;
-        const int cyf = cnt1(fj, gf.NY), jlo = max(fj - 1, 0);
-        for (int ey = -1; ey <= 1; ++ey) {
-          const int pj = fj + ey, ty = pj - 2 * Cj;
-          if (pj < 0 || pj >= gf.NY || ty < -1 || ty > 1) continue;
-          const double wzy = wz * (dy ? 0.5 : 1.0) * (ty ? 0.5 : 1.0);
-          for (int dx = -1; dx <= 1; ++dx) {
-            const int fi = 2 * I + dx;
-            if (fi < 0 || fi >= gf.NX) continue;
-            const int cxf = cnt1(fi, gf.NX), ilo = max(fi - 1, 0);
-            const long long L = (long long)cxf * cyf * czf * NDOF;
-            const long long rowbase = (long long)(NDOF * NDOF) * (block_offset(gf, fi, fj, fk) - gf.bo0);
-            for (int ex = -1; ex <= 1; ++ex) {
-              const int pi = fi + ex, tx = pi - 2 * Ci;
-              if (pi < 0 || pi >= gf.NX || tx < -1 || tx > 1) continue;
-              const double w = wzy * (dx ? 0.5 : 1.0) * (tx ? 0.5 : 1.0);
-              const int nbr = ((pk - klo) * cyf + (pj - jlo)) * cxf + (pi - ilo);
-              const double* ap = Af + rowbase + (long long)nbr * NDOF;
+    const int fk = 2 * K + dz, sk = Ck - (fk >> 1) + 1;
+    if (fk < 0 || fk >= gf.NZ || sk < ((fk & 1) ? 1 : 0) || sk > 2) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int fj = 2 * J + dy, sj = Cj - (fj >> 1) + 1;
+      if (fj < 0 || fj >= gf.NY || sj < ((fj & 1) ? 1 : 0) || sj > 2) continue;
+      const double wzy = (dz ? 0.5 : 1.0) * (dy ? 0.5 : 1.0);
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int fi = 2 * I + dx, si = Ci - (fi >> 1) + 1;
+        if (fi < 0 || fi >= gf.NX || si < ((fi & 1) ? 1 : 0) || si > 2) continue;
+        const double w = wzy * (dx ? 0.5 : 1.0);
+        const long long lf = ((long long)(fk - gf.kz0) * gf.NY + fj) * gf.NX + fi;
+        const double* bp = B + (lf * 27 + (sk * 9 + sj * 3 + si)) * (NDOF * NDOF);
 #pragma unroll
-              for (int a = 0; a < NDOF; ++a)
+        for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-                for (int b = 0; b < NDOF; ++b) acc[a][b] = fma(w, __ldg(ap + a * L + b), acc[a][b]);
-            }
-          }
-        }
+          for (int c = 0; c < NDOF; ++c) acc[a][c] = fma(w, __ldg(bp + a * NDOF + c), acc[a][c]);
       }
     }
   }
@@ -152,25 +230,55 @@ __global__ void __launch_bounds__(128) galerkin_kernel(Geo gf, Geo gc, const dou
 #pragma unroll
   for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-    for (int b = 0; b < NDOF; ++b) op[a * Lc + b] = acc[a][b];
+    for (int c = 0; c < NDOF; ++c) op[a * Lc + c] = acc[a][c];
 }
 
-extern "C" int pmb_galerkin(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* Ac, void* stream) {
+extern "C" long long pmb_galerkin_ws_doubles(const pmb_grid* pf) {
+  if (validate_grid(pf, "pmb_galerkin_ws_doubles")) return -1;
+  Geo gf = make_geo(pf);
+  return gf.nOwned * 27 * gf.ndof * gf.ndof;
+}
+
+template <int NDOF>
+static int launch_galerkin(const Geo& gf, const Geo& gc, const double* Af, double* Ac, double* B, cudaStream_t st) {
+  constexpr int T = GalCfg<NDOF>::T, STAGES = GalCfg<NDOF>::STAGES;
+  constexpr int TD = (T * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
+  const size_t smem = sizeof(double) * TD * STAGES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(galerkin_cols_kernel<NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pmb_set_error("galerkin_cols_kernel attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tpr = (gf.NX + T - 1) / T;
+  const long long ntiles = (long long)tpr * gf.NY * gf.nzl;
+  PMB_REQUIRE(ntiles < 2147483647LL, "pmb_galerkin: too many tiles");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
+  const long long nnz_bytes = 8LL * NDOF * NDOF * (pre1(gf.kz0 + gf.nzl, gf.NZ) * gf.Sy * gf.Sx - gf.bo0);
+  galerkin_cols_kernel<NDOF><<<grid, GAL_NT, smem, st>>>(gf, gc, (int)ntiles, tpr, nnz_bytes > (96LL << 20), Af, B);
+  PMB_CHECK_LAUNCH("pmb_galerkin(cols)");
+  const long long nslots = gc.nOwned * 27;
+  galerkin_rows_kernel<NDOF><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(gf, gc, B, Ac);
+  PMB_CHECK_LAUNCH("pmb_galerkin(rows)");
+  return 0;
+}
+
+extern "C" int pmb_galerkin(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* Ac, double* work, void* stream) {
   if (validate_grid(pf, "pmb_galerkin(fine)") || validate_grid(pc, "pmb_galerkin(coarse)")) return 1;
   PMB_REQUIRE(pf->nx == 2 * pc->nx && pf->ny == 2 * pc->ny && pf->nz == 2 * pc->nz && pf->ndof == pc->ndof,
               "pmb_galerkin: coarse grid is not the 2:1 coarsening of the fine grid");
-  PMB_REQUIRE(Af && Ac, "pmb_galerkin: NULL pointer argument");
+  PMB_REQUIRE(Af && Ac && work, "pmb_galerkin: NULL pointer argument");
+  PMB_REQUIRE((reinterpret_cast<size_t>(Af) & 15) == 0, "pmb_galerkin: fine data must be 16-byte aligned");
   Geo gf = make_geo(pf), gc = make_geo(pc);
-  long long nslots = gc.nOwned * 27;
-  unsigned blocks = (unsigned)((nslots + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   switch (gc.ndof) {
-    case 1: galerkin_kernel<1><<<blocks, 128, 0, st>>>(gf, gc, Af, Ac); break;
-    case 2: galerkin_kernel<2><<<blocks, 128, 0, st>>>(gf, gc, Af, Ac); break;
-    case 3: galerkin_kernel<3><<<blocks, 128, 0, st>>>(gf, gc, Af, Ac); break;
+    case 1: return launch_galerkin<1>(gf, gc, Af, Ac, work, st);
+    case 2: return launch_galerkin<2>(gf, gc, Af, Ac, work, st);
+    case 3: return launch_galerkin<3>(gf, gc, Af, Ac, work, st);
   }
-  PMB_CHECK_LAUNCH("pmb_galerkin");
-  return 0;
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------- K7

@@ -13,8 +13,7 @@
 // PARTS threads per node each take one line of the 27-point stencil (<= 3 neighbour nodes x NDOF columns for all
 // NDOF rows of the node), x is gathered through L1, the PARTS partial sums of a row are combined in fixed order
 // through shared memory and the epilogue (residual / Jacobi update / fused dot products) is applied per row.
-#include <cstdint>
-#include "pmb_common.cuh"
+#include "pmb_tilestream.cuh"
 
 enum { MODE_SPMV = PMB_SPMV, MODE_RESID = PMB_RESIDUAL, MODE_JACOBI = PMB_JACOBI, MODE_ROWSTATS = 3 };
 
@@ -37,76 +36,6 @@ template <>
 struct TileCfg<1> : TileCfgBase<1, 96, 3, 3> {};
 
 static constexpr int CTAS_PER_SM = 2;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ---- mbarrier / TMA bulk-copy primitives (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar, bool stream_hint) {
-  if (stream_hint) {
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-  } else {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-  }
-}
-
-// Tiles never straddle an x-row of nodes: tile = (row (j,k), i0 .. i0+T), so (cy, cz) are uniform per tile and a
-// node's offset inside the tile is closed-form in i alone.
-struct TileGeom {
-  int i0, ni, j, k, cy, cz, jlo, klo;
-  long long e0;  // entry offset (slab-relative) of the tile's first entry
-  long long e1;  // one past its last entry
-};
-
-template <int NDOF, int T>
-__device__ __forceinline__ TileGeom tile_geom(const Geo& g, int tile, int tiles_per_row) {
-  TileGeom t;
-  const int row = tile / tiles_per_row;
-  const int ti = tile - row * tiles_per_row;
-  const int kl = row / g.NY;
-  t.j = row - kl * g.NY;
-  t.k = kl + g.kz0;
-  t.i0 = ti * T;
-  t.ni = min(T, g.NX - t.i0);
-  t.cy = cnt1(t.j, g.NY);
-  t.cz = cnt1(t.k, g.NZ);
-  t.jlo = max(t.j - 1, 0);
-  t.klo = max(t.k - 1, 0);
-  const long long rowbase = pre1(t.k, g.NZ) * g.Sy * g.Sx + (long long)t.cz * (pre1(t.j, g.NY) * g.Sx) - g.bo0;
-  const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
-  t.e0 = (long long)(NDOF * NDOF) * rowbase + per * pre1(t.i0, g.NX);
-  t.e1 = (long long)(NDOF * NDOF) * rowbase + per * pre1(t.i0 + t.ni, g.NX);
-  return t;
-}
 
 template <int NDOF, int MODE>
 __global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)

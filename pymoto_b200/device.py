@@ -67,11 +67,19 @@ class _Workspace:
         self.dev = require_cuda()
         self.red = torch.zeros(_lib.query("pmb_ws_doubles"), dtype=torch.float64, device=self.dev)
         self._spmv_ws = None
+        self._gal_ws = None
 
     def spmv_ws(self, n):
         if self._spmv_ws is None or self._spmv_ws.numel() < n:
             self._spmv_ws = torch.empty(int(n), dtype=torch.float64, device=self.dev)
         return self._spmv_ws
+
+    def galerkin_ws(self, n):
+        """Scratch for the two-pass Galerkin product (shared by all levels: the finest level sizes it)."""
+        if self._gal_ws is None or self._gal_ws.numel() < n:
+            self._gal_ws = None
+            self._gal_ws = torch.empty(int(n), dtype=torch.float64, device=self.dev)
+        return self._gal_ws
 
 
 _workspaces = {}

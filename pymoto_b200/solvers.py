@@ -182,7 +182,8 @@ class GeometricMultigrid(Preconditioner):
             self.Ac = DeviceCSR(make_grid(nx // 2, ny // 2, nz // 2, g.ndof))
             n, nc = A.shape[0], self.Ac.shape[0]
             self._buf = dict(u=dv.empty(n), u2=dv.empty(n), t=dv.empty(n), rc=dv.empty(nc))
-        _lib.call("pmb_galerkin", g, self.Ac.grid, dv.ptr(A._buf), dv.ptr(self.Ac._buf), dv.stream())
+        work = dv.workspace().galerkin_ws(_lib.query("pmb_galerkin_ws_doubles", g))
+        _lib.call("pmb_galerkin", g, self.Ac.grid, dv.ptr(A._buf), dv.ptr(self.Ac._buf), dv.ptr(work), dv.stream())
         self.Ac.invalidate()
         if self.inner_level is None:
             self.inner_level = SolverDenseInverse()
