@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="sample grid of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event breakdown of one step (diagnostic)")
     return ap.parse_args()
 
 
@@ -224,6 +225,14 @@ def run_b200(args, full):
     # ---------------- device-resident timing
     for i in range(W):
         chain.step(xs_dev[i])
+    if args.profile and rank == 0:
+        _lib.profile_times = {}
+        chain.step(xs_dev[W])
+        prof, _lib.profile_times = _lib.profile_times, None
+        tot = sum(v[1] for v in prof.values())
+        print(f"# per-call breakdown of one step (synchronised calls), total {tot:.2f} ms", file=sys.stderr)
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            print(f"# {v[1]:9.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:5d}  avg {1e3 * v[1] / v[0]:9.1f} us  {k}", file=sys.stderr)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()

@@ -107,11 +107,27 @@ def load():
     return lib
 
 
+profile_times = None  # set to {} to time every call with CUDA events (synchronising; diagnostics only)
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise PmbError with pmb_last_error() on failure."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if profile_times is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        e1.synchronize()
+        key = (name, (args[0].nx, args[1])) if name == "pmb_spmv" else (name, args[0].nx if isinstance(args[0], Grid) else None)
+        t = profile_times.setdefault(key, [0, 0.0])
+        t[0] += 1
+        t[1] += e0.elapsed_time(e1)
+    else:
+        rc = getattr(lib, name)(*args)
     launch_count += _kernels_launched(name, args)
     key = (name, (args[0].nx, args[1])) if name == "pmb_spmv" else (name, None)
     call_stats[key] = call_stats.get(key, 0) + 1
