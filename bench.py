@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="sample grid of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="only the dominant-kernel loop (for ncu captures)")
     ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event breakdown of one step (diagnostic)")
     return ap.parse_args()
 
@@ -222,6 +223,15 @@ def run_b200(args, full):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.kernel_only:  # assemble once, then fused Jacobi sweeps on the finest level only
+        K0 = chain.asm(chain.simp(chain.flt(xs_dev[0])))
+        D0 = K0.diagonal_device()
+        va, vb, vc = dv.zeros(K0.shape[0]), dv.empty(K0.shape[0]), dv.to_device(np.random.default_rng(0).random(K0.shape[0]))
+        for _ in range(12):
+            K0.apply(_lib.JACOBI, va, vb, b=vc, diag=D0, w=0.5)
+            va, vb = vb, va
+        torch.cuda.synchronize()
+        return
     # ---------------- device-resident timing
     for i in range(W):
         chain.step(xs_dev[i])

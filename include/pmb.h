@@ -102,6 +102,11 @@ int pmb_prolong_add(const pmb_grid* gf, const pmb_grid* gc, const double* uc, do
 /* K6: Ac = R^T A R in the coarse grid's own stencil-CSR layout; work holds pmb_galerkin_ws_doubles(gf) doubles */
 int pmb_galerkin(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* Ac, double* work, void* stream);
 long long pmb_galerkin_ws_doubles(const pmb_grid* gf);
+/* the two passes separately (multi-GPU: the lower halo plane of `work`, 27*ndof^2 doubles per node stored BEFORE
+ * the pointer, is exchanged between them): cols = column collapse B = A R of the owned fine rows,
+ * rows = row collapse Ac = R^T B of the owned coarse rows */
+int pmb_galerkin_cols(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* work, void* stream);
+int pmb_galerkin_rows(const pmb_grid* gf, const pmb_grid* gc, const double* work, double* Ac, void* stream);
 
 /* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (Gauss-Jordan without
  * pivoting, valid for SPD); scratch holds 2n doubles; info (device int) is set non-zero on a non-positive pivot. */

@@ -19,8 +19,9 @@ from .filter import DensityFilter, Filter
 from .linalg import LinSolve
 from .glue import SIMP, Compliance
 from . import solvers
+from . import slab
 from ._lib import PmbError
 
 __all__ = ["Signal", "Module", "Network", "VoxelDomain", "DomainDefinition", "DeviceCSR", "DeviceDyad",
-           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "LinSolve", "SIMP", "Compliance", "solvers",
+           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "LinSolve", "SIMP", "Compliance", "solvers", "slab",
            "PmbError", "HAVE_PYMOTO"]

@@ -57,6 +57,8 @@ SIGNATURES = {
     "pmb_prolong_add": (_I, [_G, _G, _P, _P, _P]),
     "pmb_galerkin": (_I, [_G, _G, _P, _P, _P, _P]),
     "pmb_galerkin_ws_doubles": (_LL, [_G]),
+    "pmb_galerkin_cols": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_galerkin_rows": (_I, [_G, _G, _P, _P, _P]),
     "pmb_densify": (_I, [_G, _P, _P, _P]),
     "pmb_dense_invert": (_I, [_I, _P, _P, _P, _P]),
     "pmb_dense_gemv": (_I, [_I, _P, _P, _P, _P]),

@@ -14,6 +14,7 @@ from .core import Module
 from .domain import grid_dims
 from .dyad import DeviceDyad
 from .matrix import DeviceCSR, make_grid
+from . import slab
 
 
 def _strain_displacement(dN_dx):
@@ -93,25 +94,36 @@ class AssembleGeneral(Module):
         if add_constant is not None:
             raise NotImplementedError("add_constant is not supported by the B200 hot path")
         self.domain = domain
-        self.nel = domain.nel
-        self.m = self.n = self.ndof * domain.nnodes
         self.reuse_sparsity = reuse_sparsity  # the pattern is closed-form: nothing to precompute
 
         dv.require_cuda()
         nx, ny, nz = grid_dims(domain)
-        self.grid = make_grid(nx, ny, nz, self.ndof)
+        # slab decomposition (one GPU: the whole grid).  Inputs / outputs of the module are this rank's element layers.
+        self._ctx = ctx = slab.context(nz)
+        k0, k1 = ctx.part.planes(0) if ctx.active else (0, nz + 1)
+        e0, e1 = ctx.part.elem_layers(0) if ctx.active else (0, max(nz, 1))
+        self.grid = make_grid(nx, ny, nz, self.ndof, k0, k1 - k0)
+        self._lay = nx * ny  # elements per layer
+        self.nel = self._lay * (e1 - e0)
+        plane = (nx + 1) * (ny + 1) * self.ndof
+        self.m = self.n = plane * (k1 - k0)
         self._Ke_dev = dv.to_device(np.ascontiguousarray(Ke, dtype=np.float64).ravel())
 
         self.bc = None
         self.bcdiagval = bcdiagval
-        self._bcmask = None
+        self._bcmask = self._bcmask_buf = None
         if bc is not None:
-            self.bc = np.asarray(bc).ravel()
+            self.bc = np.asarray(bc).ravel()  # GLOBAL dof numbers, the same on every rank
             if bcdiagval is None:
                 self.bcdiagval = np.max(Ke)  # assembly.py:94-98
-            mask = np.zeros(self.n, dtype=np.uint8)
-            mask[self.bc] = 1
-            self._bcmask = dv.to_device(mask, torch.uint8)
+            # local mask over planes [k0-1, k1+1): the assembly kernel also looks at the column dofs in the halo planes
+            lo = (k0 - 1) * plane
+            mask = np.zeros((k1 - k0 + 2) * plane, dtype=np.uint8)
+            sel = self.bc[(self.bc >= max(lo, 0)) & (self.bc < (k1 + 1) * plane)]
+            mask[sel - lo] = 1
+            self._bcmask_buf = dv.to_device(mask, torch.uint8)
+            self._bcmask = self._bcmask_buf[plane: plane + self.n]
+        self._xbuf = None
         self._mat = None
 
     def __call__(self, xscale):
@@ -120,10 +132,16 @@ class AssembleGeneral(Module):
             raise ValueError(f"Input vector wrong size ({n}), must be equal to #nel ({self.nel})")
         self._x_on_device = dv.is_device(xscale)
         x = dv.to_device(xscale).reshape(-1)
+        if self._ctx.active:  # rows of my first node plane also need the element layer below: fetch it from the rank below
+            if self._xbuf is None:
+                self._xbuf = dv.zeros(self.nel + self._lay)
+            self._xbuf[self._lay:] = x
+            self._ctx.comm.exchange(self._xbuf, self._lay, self.nel, self._lay, lower=True, upper=False)
+            x = self._xbuf[self._lay:]
         # a fresh value buffer each call would cost 8*nnz bytes of allocation per design iteration; the matrix
         # object is reused and its cached row statistics dropped (consumers re-read it on every update()).
         if self._mat is None:
-            self._mat = DeviceCSR(self.grid, bc_mask=self._bcmask)
+            self._mat = DeviceCSR(self.grid, bc_mask=self._bcmask, comm=self._ctx.comm, level=0)
         mat = self._mat
         _lib.call("pmb_assemble", self.grid, dv.ptr(self._Ke_dev), dv.ptr(x), dv.ptr(self._bcmask),
                   float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
@@ -137,7 +155,12 @@ class AssembleGeneral(Module):
             raise TypeError("pymoto_b200.AssembleGeneral back-propagates a DeviceDyad (from pymoto_b200.LinSolve)")
         dx = dv.zeros(self.nel)
         first = True
+        mat = self._mat
         for u, v in zip(dgdmat.u, dgdmat.v):
+            if mat is not None and mat.comm is not None:  # element layer e needs node planes e and e+1
+                u, v = mat.operand(u), mat.operand(v)
+                mat.exchange(u, lower=False, upper=True)
+                mat.exchange(v, lower=False, upper=True)
             _lib.call("pmb_assemble_sens", self.grid, dv.ptr(self._Ke_dev), dv.ptr(u), dv.ptr(v), dv.ptr(self._bcmask),
                       dv.ptr(dx), 0 if first else 1, dv.stream())
             first = False

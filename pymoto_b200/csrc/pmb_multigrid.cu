@@ -240,7 +240,7 @@ extern "C" long long pmb_galerkin_ws_doubles(const pmb_grid* pf) {
 }
 
 template <int NDOF>
-static int launch_galerkin(const Geo& gf, const Geo& gc, const double* Af, double* Ac, double* B, cudaStream_t st) {
+static int launch_galerkin_cols(const Geo& gf, const Geo& gc, const double* Af, double* B, cudaStream_t st) {
   constexpr int T = GalCfg<NDOF>::T, STAGES = GalCfg<NDOF>::STAGES;
   constexpr int TD = (T * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
   const size_t smem = sizeof(double) * TD * STAGES;
@@ -258,27 +258,59 @@ static int launch_galerkin(const Geo& gf, const Geo& gc, const double* Af, doubl
   const int grid = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
   const long long nnz_bytes = 8LL * NDOF * NDOF * (pre1(gf.kz0 + gf.nzl, gf.NZ) * gf.Sy * gf.Sx - gf.bo0);
   galerkin_cols_kernel<NDOF><<<grid, GAL_NT, smem, st>>>(gf, gc, (int)ntiles, tpr, nnz_bytes > (96LL << 20), Af, B);
-  PMB_CHECK_LAUNCH("pmb_galerkin(cols)");
-  const long long nslots = gc.nOwned * 27;
-  galerkin_rows_kernel<NDOF><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(gf, gc, B, Ac);
-  PMB_CHECK_LAUNCH("pmb_galerkin(rows)");
+  PMB_CHECK_LAUNCH("pmb_galerkin_cols");
   return 0;
 }
 
-extern "C" int pmb_galerkin(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* Ac, double* work, void* stream) {
-  if (validate_grid(pf, "pmb_galerkin(fine)") || validate_grid(pc, "pmb_galerkin(coarse)")) return 1;
+template <int NDOF>
+static int launch_galerkin_rows(const Geo& gf, const Geo& gc, const double* B, double* Ac, cudaStream_t st) {
+  const long long nslots = gc.nOwned * 27;
+  galerkin_rows_kernel<NDOF><<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>(gf, gc, B, Ac);
+  PMB_CHECK_LAUNCH("pmb_galerkin_rows");
+  return 0;
+}
+
+static int check_galerkin_grids(const pmb_grid* pf, const pmb_grid* pc, const char* who) {
+  if (validate_grid(pf, who) || validate_grid(pc, who)) return 1;
   PMB_REQUIRE(pf->nx == 2 * pc->nx && pf->ny == 2 * pc->ny && pf->nz == 2 * pc->nz && pf->ndof == pc->ndof,
-              "pmb_galerkin: coarse grid is not the 2:1 coarsening of the fine grid");
-  PMB_REQUIRE(Af && Ac && work, "pmb_galerkin: NULL pointer argument");
-  PMB_REQUIRE((reinterpret_cast<size_t>(Af) & 15) == 0, "pmb_galerkin: fine data must be 16-byte aligned");
+              "%s: coarse grid is not the 2:1 coarsening of the fine grid", who);
+  // coarse plane K is produced from fine planes 2K-1 .. 2K+1: 2K and 2K+1 must be owned (2K-1 may be the lower halo)
+  PMB_REQUIRE(2 * pc->kz0 >= pf->kz0 && 2 * (pc->kz0 + pc->nzl - 1) < pf->kz0 + pf->nzl,
+              "%s: coarse slab [%d,%d) does not sit inside fine slab [%d,%d)", who, pc->kz0, pc->kz0 + pc->nzl, pf->kz0,
+              pf->kz0 + pf->nzl);
+  return 0;
+}
+
+extern "C" int pmb_galerkin_cols(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* work, void* stream) {
+  if (check_galerkin_grids(pf, pc, "pmb_galerkin_cols")) return 1;
+  PMB_REQUIRE(Af && work, "pmb_galerkin_cols: NULL pointer argument");
+  PMB_REQUIRE((reinterpret_cast<size_t>(Af) & 15) == 0, "pmb_galerkin_cols: fine data must be 16-byte aligned");
   Geo gf = make_geo(pf), gc = make_geo(pc);
   cudaStream_t st = (cudaStream_t)stream;
   switch (gc.ndof) {
-    case 1: return launch_galerkin<1>(gf, gc, Af, Ac, work, st);
-    case 2: return launch_galerkin<2>(gf, gc, Af, Ac, work, st);
-    case 3: return launch_galerkin<3>(gf, gc, Af, Ac, work, st);
+    case 1: return launch_galerkin_cols<1>(gf, gc, Af, work, st);
+    case 2: return launch_galerkin_cols<2>(gf, gc, Af, work, st);
+    case 3: return launch_galerkin_cols<3>(gf, gc, Af, work, st);
   }
   return 1;
+}
+
+extern "C" int pmb_galerkin_rows(const pmb_grid* pf, const pmb_grid* pc, const double* work, double* Ac, void* stream) {
+  if (check_galerkin_grids(pf, pc, "pmb_galerkin_rows")) return 1;
+  PMB_REQUIRE(work && Ac, "pmb_galerkin_rows: NULL pointer argument");
+  Geo gf = make_geo(pf), gc = make_geo(pc);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (gc.ndof) {
+    case 1: return launch_galerkin_rows<1>(gf, gc, work, Ac, st);
+    case 2: return launch_galerkin_rows<2>(gf, gc, work, Ac, st);
+    case 3: return launch_galerkin_rows<3>(gf, gc, work, Ac, st);
+  }
+  return 1;
+}
+
+extern "C" int pmb_galerkin(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* Ac, double* work, void* stream) {
+  if (pmb_galerkin_cols(pf, pc, Af, work, stream)) return 1;
+  return pmb_galerkin_rows(pf, pc, work, Ac, stream);
 }
 
 // ------------------------------------------------------------------------------------------------- K7

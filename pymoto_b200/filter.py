@@ -13,6 +13,7 @@ from . import device as dv
 from .core import Module
 from .domain import grid_dims
 from .matrix import make_grid
+from . import slab
 
 
 class DensityFilter(Module):
@@ -22,10 +23,18 @@ class DensityFilter(Module):
         self.radius = radius
         nx, ny, nz = grid_dims(domain)
         self.grid = make_grid(nx, ny, nz, 1)
-        self.nel = nx * ny * max(nz, 1)
-        self.nlayers = max(nz, 1)
         d = int(radius)  # window half-width, filter.py:314
         self.d = d
+        # slab decomposition: this rank filters its own element layers [e0, e1) and reads d halo layers on each side
+        self._ctx = ctx = slab.context(nz)
+        self._e0, e1 = ctx.part.elem_layers(0) if ctx.active else (0, max(nz, 1))
+        self.nlayers = e1 - self._e0
+        self._lay = nx * ny
+        self.nel = self._lay * self.nlayers
+        if ctx.active and self.nlayers < d:
+            raise ValueError(f"filter radius {radius} needs at least {d} element layers per rank (have {self.nlayers})")
+        self._pad = self._lay * d if ctx.active else 0
+        self._xbuf = dv.zeros(self.nel + 2 * self._pad) if ctx.active else None
         # cone weights exactly as the reference computes them (integer offsets -> sqrt -> max), filter.py:371-375
         rng = np.arange(-d, d + 1)
         if nz > 0:
@@ -44,7 +53,11 @@ class DensityFilter(Module):
             self.Hs = torch.where(keep, self.Hs, self.Hs.max())
 
     def _apply(self, inp, hs, out):
-        _lib.call("pmb_filter_apply", self.grid, 0, self.nlayers, self.d, dv.ptr(self._wtab), dv.ptr(inp), dv.ptr(hs),
+        if inp is not None and self._ctx.active:
+            self._xbuf[self._pad: self._pad + self.nel] = inp
+            self._ctx.comm.exchange(self._xbuf, self._pad, self.nel, self._lay, width=self.d)
+            inp = self._xbuf[self._pad: self._pad + self.nel]
+        _lib.call("pmb_filter_apply", self.grid, self._e0, self.nlayers, self.d, dv.ptr(self._wtab), dv.ptr(inp), dv.ptr(hs),
                   dv.ptr(out), dv.stream())
         return out
 

@@ -41,9 +41,14 @@ class Compliance(Module):
 
     def __call__(self, u, f):
         self._u, self._f = u, f
+        from . import slab
+
+        ctx = slab.context()
         if not dv.is_device(u):
+            if ctx.active:
+                raise TypeError("distributed runs keep nodal vectors on the device")
             return np.asarray(u) @ (f.cpu().numpy() if dv.is_device(f) else np.asarray(f))
-        return dv.dots([(u, dv.to_device(f))])[0]
+        return ctx.comm.allreduce_(dv.dots([(u, dv.to_device(f))]))[0]
 
     def _sensitivity(self, dc):
         u, f = self._u, self._f

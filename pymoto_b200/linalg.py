@@ -57,6 +57,11 @@ class LinSolve(Module):
 
     def _sensitivity(self, dfdv):
         lam = self.solver.solve(dv.to_device(dfdv), trans="T")
+        mat = self.solver.A if hasattr(self.solver, "A") else None
+        if self._u_dev.ndim == 1 and mat is not None and mat.comm is not None:
+            neg = mat.new_vec()  # halo-padded: the element sensitivity kernel reads one plane above the slab
+            dv.lincomb(neg, -1.0, lam)
+            return DeviceDyad(neg, self._u_dev), (lam if self._rhs_on_device else lam.cpu().numpy())
         if self._u_dev.ndim > 1:
             dmat = DeviceDyad([-lam[:, i].contiguous() for i in range(lam.shape[1])],
                               [self._u_dev[:, i].contiguous() for i in range(lam.shape[1])])

@@ -4,6 +4,10 @@ It is the reference's CSR matrix (``csr_matrix((data, indices, indptr))``, pymot
 the ``data`` array resident on the GPU.  On a structured voxel grid ``indptr``/``indices`` are a closed form of
 the grid, so they are only materialised (bit-exactly, int32 when nnz fits like scipy's downcast) when a user asks
 for them: ``.indptr``, ``.indices`` or ``.tocsr()``.  The solver kernels stream ``data`` alone.
+
+With a slab decomposition (pymoto_b200/slab.py) the object holds the rows of this rank's node planes; vectors it
+multiplies are views into buffers padded by one halo plane on each side (:meth:`new_vec`), refreshed from the
+neighbours by :meth:`exchange` before every operator application.
 """
 import numpy as np
 import torch
@@ -17,16 +21,19 @@ def make_grid(nx, ny, nz, ndof, kz0=0, nzl=None):
 
 
 class DeviceCSR:
-    def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None):
+    def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None, comm=None, level=0):
         dv.require_cuda()
         self.grid = grid
+        self.comm = comm if (comm is not None and comm.active and (grid.kz0 != 0 or grid.nzl != grid.nz + 1)) else None
+        self.level = level
         self.nnz = _lib.query("pmb_nnz", grid)
         self.n = _lib.query("pmb_nrows", grid)
-        self.shape = (self.n, self.n)
+        self.shape = (self.n, self.n)  # rows owned by this rank (= the whole matrix on one GPU)
         self.ndim = 2
         self.dtype = np.dtype(np.float64)
+        self.plane = (grid.nx + 1) * (grid.ny + 1) * grid.ndof  # dofs per node plane
         if data is None:
-            data = dv.empty(self.nnz + 2)  # +2: 16-byte slack read by the 128-bit streaming loads
+            data = dv.empty(self.nnz + 2)  # +2: 16-byte slack read by the 128-bit bulk copies
             data[self.nnz:] = 0.0
         assert data.is_cuda and data.dtype == torch.float64 and data.numel() >= self.nnz + 2
         assert data.data_ptr() % 16 == 0
@@ -43,6 +50,46 @@ class DeviceCSR:
     def invalidate(self):
         """Call after the values changed in place."""
         self._diag = self._nnz_off = None
+
+    # ---- vectors this operator can be applied to (halo-padded), halo refresh, global dot products
+    def new_vec(self, zero=False):
+        """Owned entries of a fresh vector whose storage carries one halo node plane on each side."""
+        base = (dv.zeros if zero else dv.empty)(self.n + 2 * self.plane)
+        if not zero and self.comm is None:
+            pass  # halos are never read on one GPU (the stencil is clipped at the grid faces)
+        elif not zero:
+            base[: self.plane] = 0.0
+            base[self.plane + self.n:] = 0.0
+        return base[self.plane: self.plane + self.n]
+
+    def exchange(self, vec, lower=True, upper=True):
+        """Refresh the halo planes of a vector made by :meth:`new_vec` from the neighbouring ranks."""
+        if self.comm is None:
+            return
+        base = vec._base if vec._base is not None else vec
+        off = vec.storage_offset()
+        if off < self.plane or base.numel() < off + self.n + self.plane or vec.numel() != self.n:
+            raise _lib.PmbError("distributed operator input must come from DeviceCSR.new_vec() (halo-padded storage)")
+        self.comm.exchange(base, off, self.n, self.plane, lower=lower, upper=upper)
+
+    def operand(self, x):
+        """``x`` itself if it can be fed to :meth:`apply` (always on one GPU; halo-padded storage when distributed),
+        else a padded copy."""
+        if self.comm is None:
+            return x
+        base = x._base
+        if base is not None and x.storage_offset() >= self.plane and base.numel() >= x.storage_offset() + self.n + self.plane:
+            return x
+        xp = self.new_vec()
+        xp.copy_(x)
+        return xp
+
+    def dots(self, pairs):
+        """Global dot products (local deterministic reduction + sum all-reduce over the slabs)."""
+        d = dv.dots(pairs)
+        if self.comm is not None:
+            self.comm.allreduce_(d)
+        return d
 
     # ---- row statistics: diagonal + number of non-zero off-diagonals, one pass over the values
     def rowstats(self):
@@ -64,13 +111,17 @@ class DeviceCSR:
         ws = None
         if dot_out is not None:
             ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles", self.grid))
+        if self.comm is not None:
+            self.exchange(x)
         _lib.call("pmb_spmv", self.grid, mode, dv.ptr(self._buf), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y),
                   dv.ptr(dotv), dv.ptr(dot_out), dv.ptr(ws), dv.stream())
+        if dot_out is not None and self.comm is not None:
+            self.comm.allreduce_(dot_out)
         return y
 
     def matvec_device(self, x, out=None):
         y = dv.empty(self.n) if out is None else out
-        return self.apply(_lib.SPMV, x, y)
+        return self.apply(_lib.SPMV, self.operand(x), y)
 
     def __matmul__(self, x):
         xd = dv.to_device(x)

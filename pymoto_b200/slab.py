@@ -1,0 +1,197 @@
+"""z-slab domain decomposition: who owns which node planes / element layers, halo exchange, scalar all-reduce.
+
+The reference is single-process; this is the multi-GPU layer of the new build (section 8e).
+Node and element numbering are z-slowest (pymoto/common/domain.py:211,224), so a slab of node planes [k0, k1) is a
+contiguous row range of K and of every nodal vector, and a contiguous range of element layers of the design.
+
+One process per GPU; collectives go through ``torch.distributed`` (NCCL on GPUs; the same code runs on gloo + CPU
+tensors, which is how the host-side logic is tested without a GPU).  The data path has exactly three exchange
+steps: (1) neighbour halo planes before an operator application / transfer / filter, (2) a sum all-reduce of the
+CG / LDAS dot products, (3) one gather of the first replicated multigrid level per V-cycle.
+"""
+import torch
+import torch.distributed as dist
+
+
+class SlabPartition:
+    """Ownership of node planes for every multigrid level.
+
+    Level 0 is the finest grid with ``nz`` elements (nz+1 node planes) in z.  Rank r owns fine planes
+    [r*m, (r+1)*m) with m = nz / world (the last rank also owns plane nz).  The first ``n_dist`` levels are split
+    that way (level l: boundaries r*m / 2**l, which must be integers and even for the next coarser split level so
+    that coarse plane K lives with fine plane 2K); all coarser levels are replicated on every rank.
+    """
+
+    def __init__(self, nz, world=1, rank=0, n_levels=1, min_planes=4, force_n_dist=None, level_dofs=None, min_dofs=0):
+        self.nz, self.world, self.rank = int(nz), int(world), int(rank)
+        if self.world > 1:
+            if self.nz <= 0:
+                raise ValueError("slab decomposition needs a 3-D grid")
+            if self.nz % self.world != 0:
+                raise ValueError(f"nz={nz} must be divisible by the number of ranks {world}")
+        self.m = self.nz // self.world if self.world > 1 else self.nz
+        # number of slab-distributed levels: planes per rank stay >= min_planes and boundaries stay integral
+        # (level l may be split only if its boundaries r*m/2**l are even, so that coarse plane K lives with fine plane 2K)
+        n_dist = 1
+        if self.world > 1:
+            if n_levels > 1 and self.m % 2 != 0:
+                raise ValueError(f"nz / ranks = {self.m} must be even for a multigrid hierarchy")
+            # the coarsest level (index n_levels-1) is solved directly and is always replicated
+            while (n_dist < n_levels - 1 and self.m % (2 ** (n_dist + 1)) == 0 and self.m // (2 ** n_dist) >= min_planes
+                   and (level_dofs is None or level_dofs[n_dist] >= min_dofs)):
+                n_dist += 1
+        else:
+            n_dist = n_levels
+        if force_n_dist is not None:
+            n_dist = force_n_dist
+        self.n_dist = n_dist
+        self.n_levels = n_levels
+
+    def is_distributed(self, level):
+        return self.world > 1 and level < self.n_dist
+
+    def planes(self, level, rank=None):
+        """Owned node planes [k0, k1) of ``rank`` at ``level`` (whole grid for replicated levels)."""
+        r = self.rank if rank is None else rank
+        nzl = self.nz >> level
+        if not self.is_distributed(level):
+            return 0, nzl + 1
+        ml = self.m >> level
+        k0 = r * ml
+        k1 = (r + 1) * ml if r < self.world - 1 else nzl + 1
+        return k0, k1
+
+    def slab_planes(self, level, rank=None):
+        """Planes [k0, k1) rank would own at ``level`` if that level were split (used at the transition to the first
+        replicated level: each rank still produces the coarse rows that sit on its fine slab)."""
+        r = self.rank if rank is None else rank
+        nzl = self.nz >> level
+        if self.world == 1:
+            return 0, nzl + 1
+        ml = self.m >> level
+        return r * ml, ((r + 1) * ml if r < self.world - 1 else nzl + 1)
+
+    def elem_layers(self, level=0, rank=None):
+        """Owned element layers [e0, e1): layer e belongs to the owner of node plane e."""
+        k0, k1 = self.planes(level, rank)
+        return k0, min(k1, self.nz >> level)
+
+    @property
+    def lower(self):
+        return self.rank - 1 if self.rank > 0 else None
+
+    @property
+    def upper(self):
+        return self.rank + 1 if self.rank < self.world - 1 else None
+
+
+class SlabComm:
+    """Neighbour halo exchange and small collectives over a torch.distributed process group."""
+
+    def __init__(self, part: SlabPartition, group=None):
+        self.part = part
+        self.group = group
+        self.exchanges = 0
+        self.allreduces = 0
+
+    @property
+    def active(self):
+        return self.part.world > 1
+
+    def exchange(self, base, own_offset, own_len, plane, lower=True, upper=True, width=1):
+        """Fill the halo planes of a padded 1-D buffer ``base`` (any dtype).
+
+        ``base[own_offset : own_offset + own_len]`` are the owned entries, ``plane`` entries per plane; the ``width``
+        planes below / above them are halos.  ``lower``: receive my lower halo (the lower neighbour sends its top
+        owned planes); ``upper``: receive my upper halo.  Every rank must call this with the same flags.
+        """
+        if not self.active:
+            return
+        p = self.part
+        n = plane * width
+        ops = []
+        if upper:  # data flows downwards: I send my bottom planes to the lower neighbour, receive from the upper
+            if p.lower is not None:
+                ops.append(dist.P2POp(dist.isend, base[own_offset:own_offset + n], p.lower, self.group))
+            if p.upper is not None:
+                ops.append(dist.P2POp(dist.irecv, base[own_offset + own_len:own_offset + own_len + n], p.upper, self.group))
+        if lower:  # data flows upwards
+            if p.upper is not None:
+                ops.append(dist.P2POp(dist.isend, base[own_offset + own_len - n:own_offset + own_len], p.upper, self.group))
+            if p.lower is not None:
+                ops.append(dist.P2POp(dist.irecv, base[own_offset - n:own_offset], p.lower, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.exchanges += 1
+
+    def allreduce_(self, t):
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.allreduces += 1
+        return t
+
+    def gather_full(self, local, full, offset):
+        """Replicate a distributed array: every rank writes its owned part at ``offset`` of the zeroed ``full``
+        buffer, then a sum all-reduce (sizes at the first replicated level are small)."""
+        full.zero_()
+        full[offset:offset + local.numel()] = local
+        return self.allreduce_(full)
+
+    def barrier(self):
+        if self.active:
+            dist.barrier(group=self.group)
+
+
+def world_from_env():
+    """(rank, world) of the default process group, (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class SlabContext:
+    """Process-wide decomposition state: the partition of the finest grid and the communicator.
+
+    Set once per process with :func:`init` (like torch.distributed's default group) so that the module signatures
+    stay exactly the reference's; without it every module runs single-GPU on the whole grid.
+    """
+
+    def __init__(self, part: SlabPartition, comm: SlabComm):
+        self.part, self.comm = part, comm
+
+    @property
+    def active(self):
+        return self.part.world > 1
+
+
+_context = None
+
+
+def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=1_000_000):
+    """Decompose ``domain`` in z over the ranks of the (default) process group. Call after init_process_group.
+
+    ``n_levels`` = number of matrices in the multigrid hierarchy (GeometricMultigrid operators + 1).  Levels with
+    fewer than ``min_dofs`` unknowns or fewer than ``min_planes`` node planes per rank are replicated on every rank.
+    """
+    global _context
+    rank, world = world_from_env()
+    nx, ny, nz = int(domain.nelx), int(domain.nely), int(getattr(domain, "nelz", 0) or 0)
+    level_dofs = [ndof * ((nx >> l) + 1) * ((ny >> l) + 1) * ((nz >> l) + 1) for l in range(max(n_levels, 1))]
+    part = SlabPartition(nz, world, rank, n_levels=n_levels, min_planes=min_planes, force_n_dist=force_n_dist,
+                         level_dofs=level_dofs, min_dofs=min_dofs)
+    _context = SlabContext(part, SlabComm(part, group))
+    return _context
+
+
+def reset():
+    global _context
+    _context = None
+
+
+def context(nz=None, n_levels=1):
+    """The active context, or a trivial single-rank one."""
+    if _context is not None:
+        return _context
+    part = SlabPartition(nz or 0, 1, 0, n_levels=n_levels)
+    return SlabContext(part, SlabComm(part))

@@ -59,8 +59,8 @@ class LinearSolver:
         xd, bd = dv.to_device(x).reshape(-1), dv.to_device(b).reshape(-1)
         assert xd.shape == bd.shape
         r = dv.empty(bd.numel())
-        A.apply(_lib.RESIDUAL, xd, r, b=bd)
-        d = dv.dots([(r, r), (bd, bd)]).cpu().numpy()
+        A.apply(_lib.RESIDUAL, A.operand(xd), r, b=bd)
+        d = A.dots([(r, r), (bd, bd)]).cpu().numpy()
         bnorm = np.sqrt(d[1]) if d[1] != 0 else 1.0
         return float(np.sqrt(d[0]) / bnorm)
 
@@ -168,6 +168,8 @@ class GeometricMultigrid(Preconditioner):
         self.sub_domain = VoxelDomain(nx // 2, ny // 2, nz // 2, domain.unitx * 2, domain.unity * 2, domain.unitz * 2)
         self.Ac = None
         self._buf = None
+        self._fine_key = None
+        self._replicate = False
         super().__init__(A)
 
     def update(self, A):
@@ -178,16 +180,54 @@ class GeometricMultigrid(Preconditioner):
             raise ValueError(f"Matrix grid {(g.nx, g.ny, g.nz)} does not match the multigrid domain {(nx, ny, nz)}")
         self.A = A
         self.smoother.update(A)
-        if self.Ac is None or self.Ac.grid.ndof != g.ndof:
-            self.Ac = DeviceCSR(make_grid(nx // 2, ny // 2, nz // 2, g.ndof))
-            n, nc = A.shape[0], self.Ac.shape[0]
-            self._buf = dict(u=dv.empty(n), u2=dv.empty(n), t=dv.empty(n), rc=dv.empty(nc))
-        work = dv.workspace().galerkin_ws(_lib.query("pmb_galerkin_ws_doubles", g))
-        _lib.call("pmb_galerkin", g, self.Ac.grid, dv.ptr(A._buf), dv.ptr(self.Ac._buf), dv.ptr(work), dv.stream())
+        if self.Ac is None or self.Ac.grid.ndof != g.ndof or self._fine_key != (g.kz0, g.nzl, A.comm is not None):
+            self._fine_key = (g.kz0, g.nzl, A.comm is not None)
+            self._setup_coarse(A)
+        gcl = self._gc_local
+        # two streaming passes; between them the lower halo plane of the column-collapsed intermediate is fetched
+        # from the rank below (its top owned fine plane contributes to my first coarse plane)
+        bplane = (g.nx + 1) * (g.ny + 1) * 27 * g.ndof * g.ndof
+        nwork = _lib.query("pmb_galerkin_ws_doubles", g)
+        work = dv.workspace().galerkin_ws(nwork + bplane)
+        st = dv.stream()
+        _lib.call("pmb_galerkin_cols", g, gcl, dv.ptr(A._buf), work.data_ptr() + 8 * bplane, st)
+        if A.comm is not None:
+            A.comm.exchange(work, bplane, nwork, bplane, lower=True, upper=False)
+        _lib.call("pmb_galerkin_rows", g, gcl, work.data_ptr() + 8 * bplane, dv.ptr(self._Ac_local._buf), st)
+        if self._replicate:  # first replicated level: every rank gets the whole coarse operator
+            A.comm.gather_full(self._Ac_local.data, self.Ac.data, self._coarse_entry_offset)
         self.Ac.invalidate()
         if self.inner_level is None:
             self.inner_level = SolverDenseInverse()
         self.inner_level.update(self.Ac)
+
+    def _setup_coarse(self, A):
+        """Coarse operator storage and level buffers (once per problem)."""
+        from . import slab
+
+        g = A.grid
+        nx, ny, nz = g.nx, g.ny, g.nz
+        n = A.shape[0]
+        if A.comm is None:  # this level lives on one GPU (single-GPU run, or a replicated level)
+            self._gc_local = make_grid(nx // 2, ny // 2, nz // 2, g.ndof)
+            self.Ac = self._Ac_local = DeviceCSR(self._gc_local, level=A.level + 1)
+            self._replicate = False
+        else:
+            part = slab.context().part
+            k0c, k1c = part.slab_planes(A.level + 1)
+            self._gc_local = make_grid(nx // 2, ny // 2, nz // 2, g.ndof, k0c, k1c - k0c)
+            self._replicate = not part.is_distributed(A.level + 1)
+            if self._replicate:
+                self._Ac_local = DeviceCSR(self._gc_local)
+                self.Ac = DeviceCSR(make_grid(nx // 2, ny // 2, nz // 2, g.ndof), level=A.level + 1)
+                self._coarse_entry_offset = 0 if k0c == 0 else _lib.query(
+                    "pmb_nnz", make_grid(nx // 2, ny // 2, nz // 2, g.ndof, 0, k0c))
+                self._coarse_row_offset = k0c * self.Ac.plane
+                self._rc_full = dv.empty(self.Ac.shape[0])
+            else:
+                self.Ac = self._Ac_local = DeviceCSR(self._gc_local, comm=A.comm, level=A.level + 1)
+        nc_local = _lib.query("pmb_nrows", self._gc_local)
+        self._buf = dict(u=A.new_vec(), u2=A.new_vec(), t=A.new_vec(), rc=dv.empty(nc_local))
 
     def solve(self, rhs, x0=None, trans="N"):
         _check_trans(trans)
@@ -200,15 +240,25 @@ class GeometricMultigrid(Preconditioner):
         if x0 is None:
             _lib.call("pmb_smooth0", n, w, dv.ptr(b), dv.ptr(D), dv.ptr(u), st)
         else:
-            A.apply(_lib.JACOBI, dv.to_device(x0).reshape(-1), u, b=b, diag=D, w=w)
+            A.apply(_lib.JACOBI, A.operand(dv.to_device(x0).reshape(-1)), u, b=b, diag=D, w=w)
         for _ in range(self.smooth_steps - 1):
             A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=w)
             u, u2 = u2, u
         # coarse-grid correction
         A.apply(_lib.RESIDUAL, u, t, b=b)
-        _lib.call("pmb_restrict", A.grid, self.Ac.grid, dv.ptr(t), dv.ptr(rc), st)
-        uc = self.inner_level.solve(rc)
-        _lib.call("pmb_prolong_add", A.grid, self.Ac.grid, dv.ptr(uc), dv.ptr(u), st)
+        A.exchange(t, lower=True, upper=False)  # restriction of coarse plane K reads fine planes 2K-1 .. 2K+1
+        _lib.call("pmb_restrict", A.grid, self._gc_local, dv.ptr(t), dv.ptr(rc), st)
+        if self._replicate:
+            A.comm.gather_full(rc, self._rc_full, self._coarse_row_offset)
+            uc_full = self.inner_level.solve(self._rc_full)
+            uc_ptr = uc_full.data_ptr() + 8 * self._coarse_row_offset  # the slab view includes its upper halo plane
+        else:
+            uc = self.inner_level.solve(rc)
+            if self.Ac.comm is not None:
+                uc = self.Ac.operand(uc)
+                self.Ac.exchange(uc, lower=False, upper=True)  # odd fine planes interpolate from coarse plane K+1
+            uc_ptr = uc.data_ptr()
+        _lib.call("pmb_prolong_add", A.grid, self._gc_local, uc_ptr, dv.ptr(u), st)
         # post-smoothing
         for _ in range(self.smooth_steps):
             A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=w)
@@ -271,13 +321,15 @@ class CG(LinearSolver):
         A, M = self.A, self.preconditioner
         n = b.numel()
         tstart = time.perf_counter()
-        x = dv.zeros(n) if x0 is None else x0.clone()
-        r, q, p = dv.empty(n), dv.empty(n), dv.empty(n)
+        x = A.new_vec(zero=x0 is None)
+        if x0 is not None:
+            x.copy_(x0)
+        r, q, p = dv.empty(n), dv.empty(n), A.new_vec()
         ws = dv.workspace()
         st = dv.stream()
 
         A.apply(_lib.RESIDUAL, x, r, b=b)
-        d = dv.dots([(r, r), (b, b)]).cpu().numpy()
+        d = A.dots([(r, r), (b, b)]).cpu().numpy()
         bnorm = np.sqrt(d[1])
         with np.errstate(divide="ignore", invalid="ignore"):
             tval = np.sqrt(d[0]) / bnorm
@@ -291,10 +343,10 @@ class CG(LinearSolver):
             return x
 
         z = M.solve(r, trans="N")
-        zz = dv.dots([(z, z)])
+        zz = A.dots([(z, z)])
         dv.lincomb(p, _lib.coef(1.0, den=dv.scalar_ptr(zz), sqrt_den=True), z)  # p = z/|z|
         d3 = dv.empty(3)   # [p.q, p.r, q.r]
-        rr = dv.empty(1)
+        rr = dv.empty(4)[:1]
         i = 0
         for i in range(self.maxit):
             A.apply(_lib.SPMV, p, q, dotv=r, dot_out=d3)
@@ -302,10 +354,12 @@ class CG(LinearSolver):
             if i % self.restart == 0:  # explicit residual
                 _lib.call("pmb_cg_xr_update", n, dv.ptr(x), None, dv.ptr(p), None, pr, pq, None, None, st)
                 A.apply(_lib.RESIDUAL, x, r, b=b)
-                rr = dv.dots([(r, r)])
+                rr = A.dots([(r, r)])
             else:
                 _lib.call("pmb_cg_xr_update", n, dv.ptr(x), dv.ptr(r), dv.ptr(p), dv.ptr(q), pr, pq, dv.ptr(rr),
                           dv.ptr(ws.red), st)
+                if A.comm is not None:
+                    A.comm.allreduce_(rr)
             tval = np.sqrt(float(rr[0].item())) / bnorm  # the only host sync of the iteration
             self.iterations, self.last_residual = i + 1, tval
             if self.verbosity >= 2:
@@ -313,7 +367,7 @@ class CG(LinearSolver):
             if tval <= self.tol:
                 break
             z = M.solve(r, trans="N")
-            qz = dv.dots([(q, z)])
+            qz = A.dots([(q, z)])
             # p = z + beta p, beta = -(q.z)/(p.q)
             dv.lincomb(p, 1.0, z, _lib.coef(-1.0, num=dv.scalar_ptr(qz), den=pq), p)
 
@@ -365,11 +419,11 @@ class LDAWrapper(LinearSolver):
 
     def _solve1(self, rhs, x0):
         A, n, st = self.A, self.A.shape[0], dv.stream()
-        sol, rhs_loc = dv.empty(n), dv.empty(n)
+        sol, rhs_loc = A.new_vec(), dv.empty(n)
         _lib.call("pmb_bc_split", n, dv.ptr(self._mask), dv.ptr(rhs), dv.ptr(self._diag), dv.ptr(sol), dv.ptr(rhs_loc), st)
         # project on the database (stored vectors are zero at the Dirichlet dofs)
         for x, b in zip(self.x_stored, self.b_stored):
-            d = dv.dots([(rhs_loc, b), (b, b)])
+            d = A.dots([(rhs_loc, b), (b, b)])
             num, den = dv.scalar_ptr(d, 0), dv.scalar_ptr(d, 1)
             dv.lincomb(rhs_loc, 1.0, rhs_loc, _lib.coef(-1.0, num=num, den=den), b)
             dv.lincomb(sol, 1.0, sol, _lib.coef(1.0, num=num, den=den), x)
@@ -381,21 +435,21 @@ class LDAWrapper(LinearSolver):
                 x0_loc = dv.empty(n)
                 _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(x0), dv.ptr(x0_loc), st)
                 for x in self.x_stored:
-                    d = dv.dots([(x0_loc, x), (x, x)])
+                    d = A.dots([(x0_loc, x), (x, x)])
                     dv.lincomb(x0_loc, 1.0, x0_loc, _lib.coef(-1.0, num=dv.scalar_ptr(d, 0), den=dv.scalar_ptr(d, 1)), x)
             xnew = self.solver.solve(rhs_loc, x0=x0_loc, trans="N")
             xadd = dv.empty(n)
             _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(xnew), dv.ptr(xadd), st)
             dv.lincomb(sol, 1.0, sol, 1.0, xadd)
             badd = dv.empty(n)
-            A.apply(_lib.SPMV, xnew, badd)
+            A.apply(_lib.SPMV, A.operand(xnew), badd)
             _lib.call("pmb_mask_zero", n, dv.ptr(self._mask), dv.ptr(badd), dv.ptr(badd), st)
             for x, b in zip(self.x_stored, self.b_stored):
-                d = dv.dots([(badd, b), (b, b)])
+                d = A.dots([(badd, b), (b, b)])
                 num, den = dv.scalar_ptr(d, 0), dv.scalar_ptr(d, 1)
                 dv.lincomb(badd, 1.0, badd, _lib.coef(-1.0, num=num, den=den), b)
                 dv.lincomb(xadd, 1.0, xadd, _lib.coef(-1.0, num=num, den=den), x)
-            bb = dv.dots([(badd, badd)])
+            bb = A.dots([(badd, badd)])
             bnrm2 = float(bb[0].item())
             if np.isfinite(bnrm2) and bnrm2 != 0:
                 inv = _lib.coef(1.0, den=dv.scalar_ptr(bb), sqrt_den=True)

@@ -394,3 +394,19 @@ def test_golden_compliance_64x32x32(pmb):
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1.0)
     x2 = dv.to_device(rng.random(dom.nel))
     assert torch.allclose(flt(x + x2), flt(x) + flt(x2), rtol=1e-13, atol=1e-13)
+
+
+def test_multi_gpu_slab_parity():
+    """z-slab path on 2 GPUs vs the oracle (skipped on a single-GPU box; run with `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "[dist_check] OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
