@@ -49,15 +49,21 @@ def parse():
     return ap.parse_args()
 
 
-def design_sequence(nel, count, seed=1234):
-    """x_0 = 0.5, then successive bounded random perturbations (seeded)."""
+def design_sequence(nel, count, seed=1234, keep=None):
+    """x_0 = 0.5, then successive bounded random perturbations (seeded).  ``keep`` maps a global design to the part a
+    rank stores (its slab); the random stream is always the global one so every rank count sees the same designs."""
     rng = np.random.default_rng(seed)
+    keep = (lambda a: a) if keep is None else keep
     x = np.full(nel, 0.5)
-    out = [x.copy()]
+    out = [keep(x).copy()]
     for _ in range(count - 1):
         x = np.clip(x + 0.2 * (rng.random(nel) - 0.5), 0.0, 1.0)
-        out.append(x.copy())
+        out.append(keep(x).copy())
     return out
+
+
+# weak scaling: the per-GPU slab stays 256x128x128-equivalent (12.8 M dof) as ranks are added
+WEAK_GRIDS = {1: (256, 128, 128), 2: (256, 128, 256), 4: (256, 256, 256), 8: (512, 256, 256)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
@@ -157,9 +163,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class GpuChain:
-    """The design iteration through the public Module API of pymoto_b200 (device-resident tensors)."""
+    """The design iteration through the public Module API of pymoto_b200 (device-resident tensors).  With more than one
+    rank the grid is split into z-slabs (pymoto_b200/slab.py) and every rank holds its own element layers / node planes."""
 
-    def __init__(self, size):
+    def __init__(self, size, world=1):
         import pymoto_b200 as pmb
         from pymoto_b200 import device as dv
 
@@ -167,19 +174,30 @@ class GpuChain:
         nx, ny, nz = size
         self.dom = dom = pmb.VoxelDomain(nx, ny, nz)
         ndof = 3
+        self.mgs = pmb.solvers.auto_multigrid(dom)
+        self.ctx = pmb.slab.init(dom, n_levels=len(self.mgs) + 1) if world > 1 else pmb.slab.context(nz)
+        k0, k1 = self.ctx.part.planes(0) if world > 1 else (0, nz + 1)
+        self.e0, self.e1 = self.ctx.part.elem_layers(0) if world > 1 else (0, nz)
+        self.lay = nx * ny
+        plane = (nx + 1) * (ny + 1) * ndof
         nodes_face = (np.arange(nz + 1)[:, None] * (ny + 1) + np.arange(ny + 1)[None, :]).ravel() * (nx + 1)  # i = 0
-        bc = (nodes_face[:, None] * ndof + np.arange(ndof)[None, :]).ravel()
-        f = np.zeros(dom.nnodes * ndof)
-        load_nodes = ((nz // 2) * (ny + 1) + np.arange(ny + 1)) * (nx + 1) + nx  # i = nx, k = nz/2
-        f[load_nodes * ndof + 2] = 1.0
+        bc = (nodes_face[:, None] * ndof + np.arange(ndof)[None, :]).ravel()  # global dof numbers
+        f = np.zeros((k1 - k0) * plane)  # this rank's node planes
+        kl = nz // 2
+        if k0 <= kl < k1:
+            load_nodes = ((kl - k0) * (ny + 1) + np.arange(ny + 1)) * (nx + 1) + nx  # i = nx, k = nz/2
+            f[load_nodes * ndof + 2] = 1.0
+        self.ndof_global = dom.nnodes * ndof
         self.f = dv.to_device(f)
         self.flt = pmb.DensityFilter(dom, radius=RADIUS)
         self.simp = pmb.SIMP(XMIN, 3)
         self.asm = pmb.AssembleStiffness(dom, bc=np.sort(bc))
-        self.mgs = pmb.solvers.auto_multigrid(dom)
         self.cg = pmb.solvers.CG(preconditioner=self.mgs[0], tol=TOL)
         self.ls = pmb.LinSolve(hermitian=True, solver=self.cg)
         self.compl = pmb.Compliance()
+
+    def local(self, x_global):
+        return x_global[self.e0 * self.lay:self.e1 * self.lay]
 
     def step(self, x):
         y = self.flt(x)
@@ -210,10 +228,10 @@ def run_b200(args, full):
     ge.build()
     from pymoto_b200 import _lib, device as dv
 
-    chain = GpuChain(full)
-    nel = chain.dom.nel
+    chain = GpuChain(full, world)
     W, K = args.warmup, args.steps
-    xs_host = design_sequence(nel, W + K)
+    xs_host = design_sequence(chain.dom.nel, W + K, keep=chain.local)
+    nel = xs_host[0].size  # elements held by this rank
     pinned = [torch.from_numpy(x).pin_memory() for x in xs_host]
     xs_dev = [p.to("cuda", non_blocking=True) for p in pinned]
     torch.cuda.synchronize()
@@ -266,7 +284,11 @@ def run_b200(args, full):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
-    value = world * K / (total_ms * 1e-3)  # replicas: every rank runs the full job (multi-GPU)
+    # one slab-decomposed job over all ranks.  Weak scaling: the grid grows with the rank count, so the whole-job
+    # throughput is quoted in 256x128x128-equivalent design iterations (iterations/s x dof / 12.83 M dof)
+    iters_per_sec = K / (total_ms * 1e-3)
+    dof_scale = chain.ndof_global / (3 * 257 * 129 * 129) if world > 1 else 1.0
+    value = iters_per_sec * dof_scale
     compl = [float(c) for c in compl]
 
     # ---------------- end to end from pinned host buffers (x in, compliance + dc/dx out)
@@ -293,7 +315,8 @@ def run_b200(args, full):
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        e2e = {"value": world * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * nel, "d2h_bytes_per_step": 8 * nel + 8}
+        e2e = {"value": dof_scale * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * nel * world,
+               "d2h_bytes_per_step": (8 * nel + 8) * world}
 
     # ---------------- roofline of the dominant kernel: fused Jacobi sweep on the finest level
     A = chain.asm._mat
@@ -321,7 +344,10 @@ def run_b200(args, full):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     fine_calls = sum(v for (name, det), v in stats.items() if name == "pmb_spmv" and det[0] == full[0])
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    # (profiles/ncu_full_tile_kernel_r1b.txt: 8.5216 GB + 0.0906 GB per launch at 256x128x128)
+    traffic = 8.5216e9 + 0.0906e9 if (tuple(full) == (256, 128, 128) and world == 1) else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "tile_kernel<3,JACOBI> (finest level)", "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes,
                 "peak_source": peak_src, "reference_layout_gbs": (12 * nnz + 4 * (n + 1) + 40 * n) / (kern_ms * 1e-3) / 1e9,
                 "fine_level_operator_launches_per_step": fine_calls / K,
@@ -343,11 +369,15 @@ def run_b200(args, full):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"3D cantilever compliance {full[0]}x{full[1]}x{full[2]} hex8 ({n} dof, nnz {nnz}), "
+            "config": {"workload": f"3D cantilever compliance {full[0]}x{full[1]}x{full[2]} hex8 ({chain.ndof_global} dof, "
+                                   f"{n} dof / nnz {nnz} per GPU), "
                                    f"SIMP p=3 xmin=1e-9, DensityFilter r=2, LDAS+CG(tol 1e-8)+GMG({len(chain.mgs)} levels, "
                                    "5+5 Jacobi w=0.5), warm start, seeded design perturbations",
                        "l2": "inputs larger than L2 (matrix values 8*nnz bytes per level-0 sweep)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} z-slabs ({chain.ctx.part.n_dist} split multigrid levels, coarser levels replicated), NCCL halo "
+                       "exchange + dot-product all-reduce; value = iterations/s x dof / 12.83M (weak scaling)",
+                       "iters_per_sec_this_grid": iters_per_sec},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "cg_iterations": cg_its, "ms_per_step_list": step_ms, "compliance": compl,
         }
@@ -358,7 +388,8 @@ def run_b200(args, full):
 
 def main():
     args = parse()
-    full = tuple(args.size) if args.size else (256, 128, 128)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    full = tuple(args.size) if args.size else WEAK_GRIDS.get(world, (256, 128, 128 * world))
     if args.impl == "reference":
         run_reference(args, full)
     else:
