@@ -8,6 +8,7 @@
  *   pmb_assemble_sens    pymoto/modules/assembly.py:298-315 -> pymoto/common/dyadcarrier.py:408-412 (einsum)
  *   pmb_rowstats         pymoto/solvers/solvers.py:88-96      (get_diagonal_indices) + iterative.py:38-39 (diagonal)
  *   pmb_spmv             scipy csr_matvec at pymoto/solvers/iterative.py:236-255,359,375,382, solvers.py:84,237
+ *   pmb_elem_spmv        the same call sites on the finest level, evaluated from x_e and Ke (assembly.py:255-261 folded in)
  *   pmb_smooth0          pymoto/solvers/iterative.py:43,233-234   (u = w r/D)
  *   pmb_restrict         pymoto/solvers/iterative.py:244      (R^T r, csc_matvec)
  *   pmb_prolong_add      pymoto/solvers/iterative.py:250      (u += R u_c, csr_matvec)
@@ -91,6 +92,15 @@ int pmb_spmv(const pmb_grid* g, int mode, const double* data, const double* x, c
 long long pmb_spmv_ws_doubles(const pmb_grid* g);
 /* workspace (doubles, zero-initialised by the caller once) for pmb_dots / pmb_cg_xr_update */
 long long pmb_ws_doubles(void);
+
+/* Matrix-free application of the FINEST-level operator K = P (sum_e s_e Ke) P + bcdiagval (I - P) from the element
+ * scaling vector s (the x that pmb_assemble was given: points at element layer kz0, layer kz0-1 read as halo) instead
+ * of the assembled values.  Same modes, epilogues and fused dot products as pmb_spmv.  Ke is a HOST pointer (it is
+ * passed to the kernel through the parameter constant bank).  ws: pmb_elem_ws_doubles(g) doubles. */
+int pmb_elem_spmv(const pmb_grid* g, int mode, const double* Ke_host, const double* s, const unsigned char* bcmask,
+                  double bcdiagval, const double* x, const double* b, const double* diag, double w, double* y,
+                  const double* dotv, double* dot_out, double* ws, void* stream);
+long long pmb_elem_ws_doubles(const pmb_grid* g);
 
 /* u = w * (r / diag) */
 int pmb_smooth0(long long n, double w, const double* r, const double* diag, double* u, void* stream);

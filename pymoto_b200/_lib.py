@@ -51,6 +51,8 @@ SIGNATURES = {
     "pmb_rowstats": (_I, [_G, _P, _P, _P, _P]),
     "pmb_spmv": (_I, [_G, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "pmb_spmv_ws_doubles": (_LL, [_G]),
+    "pmb_elem_spmv": (_I, [_G, _I, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
+    "pmb_elem_ws_doubles": (_LL, [_G]),
     "pmb_ws_doubles": (_LL, []),
     "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
     "pmb_restrict": (_I, [_G, _G, _P, _P, _P]),
@@ -85,6 +87,8 @@ def _kernels_launched(name, args):
     """How many kernels one C-ABI call launches (see the .cu sources)."""
     if name == "pmb_spmv":
         return 2 if args[9] is not None else 1  # + reduce_triples_kernel when the fused dots are requested
+    if name == "pmb_elem_spmv":
+        return 2 if args[12] is not None else 1
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":
@@ -124,14 +128,14 @@ def call(name, *args):
         rc = getattr(lib, name)(*args)
         e1.record()
         e1.synchronize()
-        key = (name, (args[0].nx, args[1])) if name == "pmb_spmv" else (name, args[0].nx if isinstance(args[0], Grid) else None)
+        key = (name, (args[0].nx, args[1])) if name in ("pmb_spmv", "pmb_elem_spmv") else (name, args[0].nx if isinstance(args[0], Grid) else None)
         t = profile_times.setdefault(key, [0, 0.0])
         t[0] += 1
         t[1] += e0.elapsed_time(e1)
     else:
         rc = getattr(lib, name)(*args)
     launch_count += _kernels_launched(name, args)
-    key = (name, (args[0].nx, args[1])) if name == "pmb_spmv" else (name, None)
+    key = (name, (args[0].nx, args[1])) if name in ("pmb_spmv", "pmb_elem_spmv") else (name, None)
     call_stats[key] = call_stats.get(key, 0) + 1
     if rc != 0:
         raise PmbError(f"{name} failed: {lib.pmb_last_error().decode()}")

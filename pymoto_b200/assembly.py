@@ -107,7 +107,8 @@ class AssembleGeneral(Module):
         self.nel = self._lay * (e1 - e0)
         plane = (nx + 1) * (ny + 1) * self.ndof
         self.m = self.n = plane * (k1 - k0)
-        self._Ke_dev = dv.to_device(np.ascontiguousarray(Ke, dtype=np.float64).ravel())
+        self._Ke_host = np.ascontiguousarray(Ke, dtype=np.float64).ravel().copy()
+        self._Ke_dev = dv.to_device(self._Ke_host)
 
         self.bc = None
         self.bcdiagval = bcdiagval
@@ -132,12 +133,14 @@ class AssembleGeneral(Module):
             raise ValueError(f"Input vector wrong size ({n}), must be equal to #nel ({self.nel})")
         self._x_on_device = dv.is_device(xscale)
         x = dv.to_device(xscale).reshape(-1)
-        if self._ctx.active:  # rows of my first node plane also need the element layer below: fetch it from the rank below
-            if self._xbuf is None:
-                self._xbuf = dv.zeros(self.nel + self._lay)
-            self._xbuf[self._lay:] = x
+        # private copy of the scaling vector (it also generates the matrix-free finest-level operator until the next
+        # call) with room for the element layer below my first node plane, fetched from the rank below
+        if self._xbuf is None:
+            self._xbuf = dv.zeros(self.nel + self._lay)
+        self._xbuf[self._lay:] = x
+        if self._ctx.active:
             self._ctx.comm.exchange(self._xbuf, self._lay, self.nel, self._lay, lower=True, upper=False)
-            x = self._xbuf[self._lay:]
+        x = self._xbuf[self._lay:]
         # a fresh value buffer each call would cost 8*nnz bytes of allocation per design iteration; the matrix
         # object is reused and its cached row statistics dropped (consumers re-read it on every update()).
         if self._mat is None:
@@ -146,6 +149,8 @@ class AssembleGeneral(Module):
         _lib.call("pmb_assemble", self.grid, dv.ptr(self._Ke_dev), dv.ptr(x), dv.ptr(self._bcmask),
                   float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
         mat.invalidate()
+        mat.generator = dict(ke=self._Ke_host, s=x, mask=self._bcmask,
+                             bcdiag=float(self.bcdiagval if self.bcdiagval is not None else 0.0))
         return mat
 
     def _sensitivity(self, dgdmat):

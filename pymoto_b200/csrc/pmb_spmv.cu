@@ -206,25 +206,6 @@ __global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)
   }
 }
 
-// final deterministic reduction of the per-CTA partial triples
-__global__ void __launch_bounds__(1024) reduce_triples_kernel(const double* __restrict__ partials, long long nblocks,
-                                                               double* __restrict__ out) {
-  __shared__ double s[3][32];
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (long long v = threadIdx.x; v < nblocks; v += 1024)
-    a0 += partials[3 * v], a1 += partials[3 * v + 1], a2 += partials[3 * v + 2];
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  if ((threadIdx.x & 31) == 0) s[0][threadIdx.x >> 5] = a0, s[1][threadIdx.x >> 5] = a1, s[2][threadIdx.x >> 5] = a2;
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double t = 0.0;
-    for (int v = 0; v < 32; ++v) t += s[threadIdx.x][v];
-    out[threadIdx.x] = t;
-  }
-}
-
 static int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -21,6 +21,11 @@ def make_grid(nx, ny, nz, ndof, kz0=0, nzl=None):
 
 
 class DeviceCSR:
+    # Apply finest-level operators matrix-free (from the element scaling vector, pmb_elem.cu) when the assembly module
+    # attached its generator; the assembled values stay the source of truth for everything else.  Set to False to
+    # stream the CSR values on every level.
+    matrix_free = True
+
     def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None, comm=None, level=0):
         dv.require_cuda()
         self.grid = grid
@@ -41,6 +46,7 @@ class DeviceCSR:
         self.bc_mask = bc_mask  # uint8 per dof or None (set by the assembly module; informational)
         self._indptr = self._indices = None
         self._diag = self._nnz_off = None
+        self.generator = None  # dict(ke=host ndarray, s=device tensor, mask=device uint8 or None, bcdiag=float)
 
     # ---- values
     @property
@@ -108,13 +114,19 @@ class DeviceCSR:
     # ---- products
     def apply(self, mode, x, y, b=None, diag=None, w=0.0, dotv=None, dot_out=None):
         """Raw kernel call on device tensors: y = A x | b - A x | x + w (b - A x)/diag, optional fused dots."""
+        gen = self.generator if DeviceCSR.matrix_free else None
         ws = None
         if dot_out is not None:
-            ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles", self.grid))
+            ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles" if gen is None else "pmb_elem_ws_doubles", self.grid))
         if self.comm is not None:
             self.exchange(x)
-        _lib.call("pmb_spmv", self.grid, mode, dv.ptr(self._buf), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y),
-                  dv.ptr(dotv), dv.ptr(dot_out), dv.ptr(ws), dv.stream())
+        if gen is None:
+            _lib.call("pmb_spmv", self.grid, mode, dv.ptr(self._buf), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y),
+                      dv.ptr(dotv), dv.ptr(dot_out), dv.ptr(ws), dv.stream())
+        else:
+            _lib.call("pmb_elem_spmv", self.grid, mode, gen["ke"].ctypes.data, dv.ptr(gen["s"]), dv.ptr(gen["mask"]),
+                      float(gen["bcdiag"]), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y), dv.ptr(dotv),
+                      dv.ptr(dot_out), dv.ptr(ws), dv.stream())
         if dot_out is not None and self.comm is not None:
             self.comm.allreduce_(dot_out)
         return y
