@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) elem_kernel(Geo g, const __grid_constant_
   constexpr int BX = 32, BY = DIM3 ? 4 : 8, BZ = DIM3 ? 2 : 1;
   constexpr int TX = BX + 2, TY = BY + 2, TZ = DIM3 ? BZ + 2 : 1;
   constexpr int SZ = DIM3 ? BZ + 1 : 1;
-  constexpr int LD = KeParam<NDOF, DIM3>::LD, NN = KeParam<NDOF, DIM3>::NN;
+  constexpr int LD = KeParam<NDOF, DIM3>::LD;
   __shared__ double su[TZ][TY][TX * NDOF];
   __shared__ double ss[SZ][BY + 1][BX + 1];
   __shared__ double wred[3][8];
@@ -39,86 +39,138 @@ __global__ void __launch_bounds__(256) elem_kernel(Geo g, const __grid_constant_
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, kl0 = blockIdx.z * BZ;  // kl0: plane index relative to kz0
 
-  // ---- stage the masked input vector of the brick + 1-node apron (zero outside the grid)
-  for (int q = tid; q < TZ * TY * TX; q += 256) {
-    const int tx = q % TX, ty = (q / TX) % TY, tz = q / (TX * TY);
-    const int i = i0 - 1 + tx, j = j0 - 1 + ty, k = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
-    const bool in = i >= 0 && i < g.NX && j >= 0 && j < g.NY && k >= 0 && k < g.NZ;
-    const long long ln = ((long long)(k - g.kz0) * g.NY + j) * g.NX + i;
+  // ---- stage the masked input vector of the brick + 1-node apron (zero outside the grid).  A (tz, ty) row of the
+  //      brick is TX*NDOF contiguous doubles of x: two rows per pass, 128 threads each, no per-element index division
+  constexpr int ROWLEN = TX * NDOF;
+  static_assert(ROWLEN <= 128, "row of the staged brick must fit 128 threads");
+  // (loads are branch-free: out-of-grid slots read a safe in-range address and are zeroed by a select, so all of a
+  //  thread's loads are in flight together)
+  const long long safe = (((long long)kl0 * g.NY + j0) * g.NX + i0) * NDOF;  // first dof of the brick: always owned
+  {
+    const int col = tid & 127, half = tid >> 7;
+    const int i = i0 - 1 + col / NDOF;
+    const bool colin = col < ROWLEN && i >= 0 && i < g.NX;
+    double xv[(TZ * TY + 1) / 2];
+    unsigned char mk[(TZ * TY + 1) / 2];
+    bool inb[(TZ * TY + 1) / 2];
 #pragma unroll
-    for (int d = 0; d < NDOF; ++d) {
-      double v = 0.0;
-      if (in && !(mask && mask[ln * NDOF + d])) v = __ldg(x + ln * NDOF + d);
-      su[tz][ty][tx * NDOF + d] = v;
+    for (int q = 0; q < (TZ * TY + 1) / 2; ++q) {
+      const int row = 2 * q + half;
+      const int ty = row % TY, tz = row / TY;
+      const int j = j0 - 1 + ty, k = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
+      inb[q] = colin && row < TZ * TY && j >= 0 && j < g.NY && k >= 0 && k < g.NZ;
+      const long long idx = inb[q] ? (((long long)(k - g.kz0) * g.NY + j) * g.NX + (i0 - 1)) * NDOF + col : safe;
+      xv[q] = __ldg(x + idx);
+      mk[q] = mask ? __ldg(mask + idx) : (unsigned char)0;
+    }
+#pragma unroll
+    for (int q = 0; q < (TZ * TY + 1) / 2; ++q) {
+      const int row = 2 * q + half;
+      if (col < ROWLEN && row < TZ * TY) su[row / TY][row % TY][col] = (inb[q] && !mk[q]) ? xv[q] : 0.0;
     }
   }
   // ---- stage the element densities: slot (tz,ty,tx) = element (i0-1+tx, j0-1+ty, k-1+tz)
-  for (int q = tid; q < SZ * (BY + 1) * (BX + 1); q += 256) {
-    const int tx = q % (BX + 1), ty = (q / (BX + 1)) % (BY + 1), tz = q / ((BX + 1) * (BY + 1));
-    const int ei = i0 - 1 + tx, ej = j0 - 1 + ty, ek = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
-    double v = 0.0;
-    if (ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE)
-      v = __ldg(s + ((long long)(ek - (DIM3 ? g.kz0 : 0)) * g.ny + ej) * g.nx + ei);
-    ss[tz][ty][tx] = v;
+  {
+    constexpr int NS = SZ * (BY + 1) * (BX + 1);
+    double sv[(NS + 255) / 256];
+    bool sin[(NS + 255) / 256];
+#pragma unroll
+    for (int q = 0; q < (NS + 255) / 256; ++q) {
+      const int p = tid + 256 * q;
+      const int tx = p % (BX + 1), ty = (p / (BX + 1)) % (BY + 1), tz = p / ((BX + 1) * (BY + 1));
+      const int ei = i0 - 1 + tx, ej = j0 - 1 + ty, ek = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
+      sin[q] = p < NS && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE;
+      // safe address: an element of the brick's own first node (exists unless the brick starts on the far faces)
+      const long long sidx = sin[q] ? ((long long)(ek - (DIM3 ? g.kz0 : 0)) * g.ny + ej) * g.nx + ei : 0;
+      sv[q] = __ldg(s + sidx);
+    }
+#pragma unroll
+    for (int q = 0; q < (NS + 255) / 256; ++q) {
+      const int p = tid + 256 * q;
+      if (p < NS) ss[p / ((BX + 1) * (BY + 1))][(p / (BX + 1)) % (BY + 1)][p % (BX + 1)] = sin[q] ? sv[q] : 0.0;
+    }
   }
-  __syncthreads();
 
   const int tx = tid % BX, ty = (tid / BX) % BY, tz = tid / (BX * BY);
   const int i = i0 + tx, j = j0 + ty, kl = kl0 + tz;
   const bool valid = i < g.NX && j < g.NY && kl < g.nzl;
+  const long long ln = ((long long)kl * g.NY + j) * g.NX + i;
 
+  // ---- epilogue operands of this thread's rows: issued now, consumed after the FMA phase
+  double xr[NDOF], br[NDOF], dr[NDOF], dvr[NDOF];
+  bool mr[NDOF];
+#pragma unroll
+  for (int d = 0; d < NDOF; ++d) {
+    const long long r = valid ? ln * NDOF + d : safe;
+    mr[d] = mask && __ldg(mask + r);
+    xr[d] = __ldg(x + r);
+    br[d] = (MODE != EMODE_SPMV) ? __ldg(b + r) : 0.0;
+    dr[d] = (MODE == EMODE_JACOBI) ? __ldg(diag + r) : 1.0;
+    dvr[d] = (partials && dotv) ? __ldg(dotv + r) : 0.0;
+  }
+  __syncthreads();
+
+  // ---- t[e][d] = sum over the nodes m of element e of Ke[a(e), b(e,m)] u_m : every neighbour value is read from
+  //      shared memory once and used by all elements that contain it (compile-time Ke indices -> constant-bank operands)
+  constexpr int NE = DIM3 ? 8 : 4;
+  double t[NE][NDOF];
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d) t[e][d] = 0.0;
+  if (valid) {
+#pragma unroll
+    for (int dk = (DIM3 ? -1 : 0); dk <= (DIM3 ? 1 : 0); ++dk)
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+          const double* up = &su[DIM3 ? tz + 1 + dk : 0][ty + 1 + dj][(tx + 1 + di) * NDOF];
+          double uv[NDOF];
+#pragma unroll
+          for (int c = 0; c < NDOF; ++c) uv[c] = up[c];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;  // element (i-1+ox, j-1+oy, k-1+oz)
+            const int ax = 1 - ox, ay = 1 - oy, az = DIM3 ? 1 - oz : 0;  // local position of this node in it
+            const int bx = ax + di, by = ay + dj, bz = az + dk;           // local position of the neighbour in it
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > (DIM3 ? 1 : 0)) continue;
+            const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+              for (int d = 0; d < NDOF; ++d) t[e][d] = fma(ke.v[(a * NDOF + d) * LD + bn * NDOF + c], uv[c], t[e][d]);
+          }
+        }
+  }
   double acc[NDOF];
 #pragma unroll
   for (int d = 0; d < NDOF; ++d) acc[d] = 0.0;
   if (valid) {
 #pragma unroll
-    for (int oz = 0; oz < (DIM3 ? 2 : 1); ++oz)
+    for (int e = 0; e < NE; ++e) {
+      const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
+      const double se = ss[DIM3 ? tz + oz : 0][ty + oy][tx + ox];
 #pragma unroll
-      for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-        for (int ox = 0; ox < 2; ++ox) {
-          const double se = ss[tz + oz][ty + oy][tx + ox];
-          const int a = (1 - ox) + 2 * (1 - oy) + (DIM3 ? 4 * (1 - oz) : 0);
-          double t[NDOF];
-#pragma unroll
-          for (int d = 0; d < NDOF; ++d) t[d] = 0.0;
-#pragma unroll
-          for (int bn = 0; bn < NN; ++bn) {
-            const int bx = bn & 1, by = (bn >> 1) & 1, bz = (bn >> 2) & 1;
-            const double* up = &su[tz + oz + bz][ty + oy + by][(tx + ox + bx) * NDOF];
-#pragma unroll
-            for (int c = 0; c < NDOF; ++c) {
-              const double uv = up[c];
-#pragma unroll
-              for (int d = 0; d < NDOF; ++d) t[d] = fma(ke.v[(a * NDOF + d) * LD + bn * NDOF + c], uv, t[d]);
-            }
-          }
-#pragma unroll
-          for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, t[d], acc[d]);
-        }
+      for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, t[e][d], acc[d]);
+    }
   }
 
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   if (valid) {
-    const long long ln = ((long long)kl * g.NY + j) * g.NX + i;
 #pragma unroll
     for (int d = 0; d < NDOF; ++d) {
       const long long r = ln * NDOF + d;
-      const bool m = mask && mask[r];
-      const double xr = (m || MODE == EMODE_JACOBI || partials) ? x[r] : 0.0;
-      const double ax = m ? bcdiag * xr : acc[d];
+      const double ax = mr[d] ? bcdiag * xr[d] : acc[d];
       double out;
       if (MODE == EMODE_SPMV) out = ax;
-      else if (MODE == EMODE_RESID) out = b[r] - ax;
-      else out = xr + w * ((b[r] - ax) / diag[r]);
+      else if (MODE == EMODE_RESID) out = br[d] - ax;
+      else out = xr[d] + w * ((br[d] - ax) / dr[d]);
       y[r] = out;
       if (partials) {
-        d0 = fma(out, xr, d0);
-        if (dotv) {
-          const double dv = dotv[r];
-          d1 = fma(xr, dv, d1);
-          d2 = fma(out, dv, d2);
-        }
+        d0 = fma(out, xr[d], d0);
+        d1 = fma(xr[d], dvr[d], d1);
+        d2 = fma(out, dvr[d], d2);
       }
     }
   }
