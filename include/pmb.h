@@ -118,10 +118,12 @@ long long pmb_galerkin_ws_doubles(const pmb_grid* gf);
 int pmb_galerkin_cols(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* work, void* stream);
 int pmb_galerkin_rows(const pmb_grid* gf, const pmb_grid* gc, const double* work, double* Ac, void* stream);
 
-/* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (Gauss-Jordan without
- * pivoting, valid for SPD); scratch holds 2n doubles; info (device int) is set non-zero on a non-positive pivot. */
+/* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (blocked Gauss-Jordan without
+ * pivoting, valid for SPD); scratch holds pmb_dense_invert_ws_doubles(n) doubles; info (device int) is set non-zero
+ * on a non-positive pivot. */
 int pmb_densify(const pmb_grid* g, const double* data, double* dense, void* stream);
 int pmb_dense_invert(int n, double* dense, double* scratch, int* info, void* stream);
+long long pmb_dense_invert_ws_doubles(int n);
 int pmb_dense_gemv(int n, const double* M, const double* x, double* y, void* stream);
 
 /* K8: out[i] = sum a_i . b_i for i < k (k <= 4), deterministic (fixed partial order). */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pmb_galerkin_rows": (_I, [_G, _G, _P, _P, _P]),
     "pmb_densify": (_I, [_G, _P, _P, _P]),
     "pmb_dense_invert": (_I, [_I, _P, _P, _P, _P]),
+    "pmb_dense_invert_ws_doubles": (_LL, [_I]),
     "pmb_dense_gemv": (_I, [_I, _P, _P, _P, _P]),
     "pmb_dots": (_I, [_LL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pmb_lincomb": (_I, [_LL, _P, Coef, _P, Coef, _P, _P]),
@@ -92,7 +93,7 @@ def _kernels_launched(name, args):
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":
-        return 2 * int(args[0])  # one copy + one update kernel per Gauss-Jordan step
+        return 3 * ((int(args[0]) + 31) // 32)  # pivot block + panels + rank-32 update per 32 pivots
     return 1
 
 

@@ -53,7 +53,7 @@ extern "C" int pmb_csr_pattern(const pmb_grid* p, void* indptr, void* indices, i
 }
 
 // ------------------------------------------------------------------------------------------------- K1
-// One thread per (row, neighbour slot): NDOF consecutive CSR entries.
+// One thread per (node, neighbour slot): the NDOF x NDOF block A[n, c] (NDOF runs of NDOF consecutive CSR entries).
 template <int NDOF>
 __global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __restrict__ Ke, const double* __restrict__ x,
                                                         const unsigned char* __restrict__ bcmask, double bcdiagval,
@@ -65,12 +65,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __re
   __syncthreads();
 
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long nslots = g.nOwned * NDOF * 27;
+  long long nslots = g.nOwned * 27;
   if (t >= nslots) return;
   int s = (int)(t % 27);
-  long long r = t / 27;
-  long long ln = r / NDOF;
-  int d = (int)(r - ln * NDOF);
+  long long ln = t / 27;
   int i, j, k;
   node_ijk(g, ln, i, j, k);
   int dk = s / 9 - 1, dj = (s / 3) % 3 - 1, di = s % 3 - 1;
@@ -80,15 +78,16 @@ __global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __re
   int ilo = max(i - 1, 0), jlo = max(j - 1, 0), klo = max(k - 1, 0);
   long long L = (long long)cx * cy * cz * NDOF;
   int nbr = ((ck - klo) * cy + (cj - jlo)) * cx + (ci - ilo);
-  long long off = (long long)(NDOF * NDOF) * (block_offset(g, i, j, k) - g.bo0) + d * L + (long long)nbr * NDOF;
+  long long off = (long long)(NDOF * NDOF) * (block_offset(g, i, j, k) - g.bo0) + (long long)nbr * NDOF;
 
-  // local (slab-relative) dof numbers for the bc mask: row node ln, column node lc (may lie in a halo plane)
+  // local (slab-relative) node numbers for the bc mask: row node ln, column node lc (may lie in a halo plane)
   long long lc = ((long long)(ck - g.kz0) * g.NY + cj) * g.NX + ci;
-  bool rowbc = bcmask && bcmask[ln * NDOF + d];
 
-  double acc[NDOF];
+  double acc[NDOF][NDOF];
 #pragma unroll
-  for (int cd = 0; cd < NDOF; ++cd) acc[cd] = 0.0;
+  for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+    for (int cd = 0; cd < NDOF; ++cd) acc[d][cd] = 0.0;
 
   const int nzo = g.dim3 ? 2 : 1;
   for (int oz = 0; oz < nzo; ++oz) {
@@ -106,21 +105,29 @@ __global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __re
         long long e = ((long long)(ek - g.kz0) * g.ny + ej) * g.nx + ei;
         double xe = __ldg(x + e);
         int a = ax + 2 * ay + 4 * az, b = bx + 2 * by + 4 * bz;
-        const double* kp = sKe + (a * NDOF + d) * ke_ld + b * NDOF;
+        const double* kp = sKe + (a * NDOF) * ke_ld + b * NDOF;
+        // ascending element number, separate multiply and add: the order and rounding of np.add.at (assembly.py:267-268)
 #pragma unroll
-        for (int cd = 0; cd < NDOF; ++cd) acc[cd] = __dadd_rn(acc[cd], __dmul_rn(kp[cd], xe));
+        for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+          for (int cd = 0; cd < NDOF; ++cd) acc[d][cd] = __dadd_rn(acc[d][cd], __dmul_rn(kp[d * ke_ld + cd], xe));
       }
     }
   }
+  bool rowbc[NDOF], colbc[NDOF];
 #pragma unroll
-  for (int cd = 0; cd < NDOF; ++cd) {
-    double v = acc[cd];
-    if (bcmask) {
-      bool colbc = bcmask[lc * NDOF + cd];
-      if (rowbc || colbc) v = (lc == ln && cd == d) ? bcdiagval : 0.0;
-    }
-    data[off + cd] = v;
+  for (int d = 0; d < NDOF; ++d) {
+    rowbc[d] = bcmask && bcmask[ln * NDOF + d];
+    colbc[d] = bcmask && bcmask[lc * NDOF + d];
   }
+#pragma unroll
+  for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+    for (int cd = 0; cd < NDOF; ++cd) {
+      double v = acc[d][cd];
+      if (rowbc[d] || colbc[cd]) v = (lc == ln && cd == d) ? bcdiagval : 0.0;
+      data[off + d * L + cd] = v;
+    }
 }
 
 extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke, const double* x, const unsigned char* bcmask,
@@ -128,7 +135,7 @@ extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke, const double* x
   if (validate_grid(p, "pmb_assemble")) return 1;
   PMB_REQUIRE(Ke && x && data, "pmb_assemble: NULL pointer argument");
   Geo g = make_geo(p);
-  long long nslots = g.nOwned * g.ndof * 27;
+  long long nslots = g.nOwned * 27;
   unsigned blocks = (unsigned)((nslots + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   switch (g.ndof) {

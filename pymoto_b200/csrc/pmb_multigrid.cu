@@ -89,7 +89,8 @@ extern "C" int pmb_prolong_add(const pmb_grid* pf, const pmb_grid* pc, const dou
 //                     nodes C around it; the fine matrix is streamed once through the same TMA tile ring as the
 //                     operator kernel and each (i, C) block is gathered from shared memory;
 //   pass 2 (rows):    Ac[I, C] = sum_{i in supp(I)} w_I(i) B[i, C], written straight into the coarse stencil-CSR layout.
-// B is stored padded: 27 coarse slots x NDOF^2 per fine node (slot = per-dimension offset C - (f >> 1) + 1).
+// B is stored padded as [fine node][NDOF^2][27 coarse slots] (slot = per-dimension offset C - (f >> 1) + 1), so that
+// the threads of a warp (consecutive slots) store and load consecutive doubles.
 template <int NDOF>
 struct GalCfg;
 template <>
@@ -170,11 +171,12 @@ __global__ void __launch_bounds__(GAL_NT, 2) galerkin_cols_kernel(Geo gf, Geo gc
           }
         }
       }
-      double* bp = B + ((lnode0 + gI) * 27 + slot) * (NDOF * NDOF);
+      // B layout [fine node][NDOF*NDOF][27 slots]: consecutive threads (slots) store consecutive doubles
+      double* bp = B + (lnode0 + gI) * (27 * NDOF * NDOF) + slot;
 #pragma unroll
       for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-        for (int c = 0; c < NDOF; ++c) bp[a * NDOF + c] = acc[a][c];
+        for (int c = 0; c < NDOF; ++c) bp[(a * NDOF + c) * 27] = acc[a][c];
     }
     __syncthreads();
     if (tid == 0 && it + STAGES < my_tiles) {
@@ -214,11 +216,11 @@ __global__ void __launch_bounds__(128) galerkin_rows_kernel(Geo gf, Geo gc, cons
         if (fi < 0 || fi >= gf.NX || si < ((fi & 1) ? 1 : 0) || si > 2) continue;
         const double w = wzy * (dx ? 0.5 : 1.0);
         const long long lf = ((long long)(fk - gf.kz0) * gf.NY + fj) * gf.NX + fi;
-        const double* bp = B + (lf * 27 + (sk * 9 + sj * 3 + si)) * (NDOF * NDOF);
+        const double* bp = B + lf * (27 * NDOF * NDOF) + (sk * 9 + sj * 3 + si);
 #pragma unroll
         for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-          for (int c = 0; c < NDOF; ++c) acc[a][c] = fma(w, __ldg(bp + a * NDOF + c), acc[a][c]);
+          for (int c = 0; c < NDOF; ++c) acc[a][c] = fma(w, __ldg(bp + (a * NDOF + c) * 27), acc[a][c]);
       }
     }
   }
@@ -351,35 +353,74 @@ extern "C" int pmb_densify(const pmb_grid* p, const double* data, double* dense,
   return 0;
 }
 
-// In-place Gauss-Jordan inverse without pivoting (SPD input => positive pivots), one elimination step per
-// launch pair so the whole GPU works on every step (the matrix, <= ~30 MB, stays in L2).
-__global__ void gj_copy_kernel(int n, int k, const double* __restrict__ A, double* __restrict__ rowk, double* __restrict__ colk,
-                               int* __restrict__ info) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) {
-    rowk[t] = A[(long long)k * n + t];
-    colk[t] = A[(long long)t * n + k];
+// In-place BLOCKED Gauss-Jordan inverse without pivoting (SPD input => every pivot block is SPD).  Per block of 32
+// pivots: (1) one CTA inverts the 32x32 pivot block P = inv(A_kk) in shared memory, (2) the pivot row panel becomes
+// R = P A_k,: (R_k,k = P) while the old pivot column panel C = A_:,k is saved, (3) one rank-32 update of the whole
+// matrix: rows of the block <- R, every other row i: A_i,: <- (A_i,: with the block columns zeroed) - C_i R.
+// 3 launches per 32 pivots instead of 2 per pivot; the matrix (<= a few 10 MB) stays in L2.
+static constexpr int GJB = 32;
+
+__global__ void __launch_bounds__(GJB* GJB) gj_pivot_block_kernel(int n, int k0, int bs, const double* __restrict__ A,
+                                                                   double* __restrict__ P, int* __restrict__ info) {
+  __shared__ double M[GJB][GJB + 1];
+  const int tx = threadIdx.x % GJB, ty = threadIdx.x / GJB;
+  const bool act = tx < bs && ty < bs;
+  M[ty][tx] = act ? A[(long long)(k0 + ty) * n + (k0 + tx)] : (tx == ty ? 1.0 : 0.0);
+  for (int k = 0; k < bs; ++k) {
+    __syncthreads();
+    const double piv = M[k][k];
+    const double rk = (tx == k ? 1.0 : M[k][tx]) / piv;
+    const double ck = M[ty][k];
+    const double cur = (tx == k) ? 0.0 : M[ty][tx];
+    if (threadIdx.x == 0 && !(piv > 0.0) && *info == 0) *info = k0 + k + 1;
+    __syncthreads();
+    M[ty][tx] = (ty == k) ? rk : cur - ck * rk;
   }
-  if (t == 0) {
-    double p = A[(long long)k * n + k];
-    if (!(p > 0.0) && *info == 0) *info = k + 1;
-  }
+  __syncthreads();
+  if (act) P[ty * GJB + tx] = M[ty][tx];
 }
 
-__global__ void __launch_bounds__(256) gj_update_kernel(int n, int k, double* __restrict__ A, const double* __restrict__ rowk,
-                                                         const double* __restrict__ colk) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y;
+// R[t][j] = (P A_k,:)[t][j] outside the block columns, P inside; C[i][t] = A[i][k0+t]
+__global__ void __launch_bounds__(256) gj_panels_kernel(int n, int k0, int bs, const double* __restrict__ A,
+                                                         const double* __restrict__ P, double* __restrict__ R,
+                                                         double* __restrict__ C) {
+  __shared__ double sP[GJB * GJB];
+  for (int q = threadIdx.x; q < GJB * GJB; q += 256) sP[q] = P[q];
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= n) return;
-  const double p = rowk[k];
-  const double rk = (j == k ? 1.0 : rowk[j]) / p;
-  if (i == k) {
-    A[(long long)i * n + j] = rk;
-  } else {
-    const double aij = (j == k) ? 0.0 : A[(long long)i * n + j];
-    A[(long long)i * n + j] = aij - colk[i] * rk;
+  double col[GJB];
+#pragma unroll 8
+  for (int t = 0; t < bs; ++t) col[t] = A[(long long)(k0 + t) * n + j];
+  const bool inblk = j >= k0 && j < k0 + bs;
+  for (int t = 0; t < bs; ++t) {
+    double acc = 0.0;
+    if (inblk) acc = sP[t * GJB + (j - k0)];
+    else
+      for (int q = 0; q < bs; ++q) acc = fma(sP[t * GJB + q], col[q], acc);
+    R[(long long)t * n + j] = acc;
   }
+  // old pivot column panel (thread j doubles as row index i = j)
+  for (int t = 0; t < bs; ++t) C[(long long)j * GJB + t] = A[(long long)j * n + (k0 + t)];
 }
+
+__global__ void __launch_bounds__(256) gj_rank_update_kernel(int n, int k0, int bs, double* __restrict__ A,
+                                                              const double* __restrict__ R, const double* __restrict__ C) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  if (i >= k0 && i < k0 + bs) {
+    A[(long long)i * n + j] = R[(long long)(i - k0) * n + j];
+    return;
+  }
+  const bool inblk = j >= k0 && j < k0 + bs;
+  double acc = inblk ? 0.0 : A[(long long)i * n + j];
+  const double* ci = C + (long long)i * GJB;
+  for (int t = 0; t < bs; ++t) acc = fma(-ci[t], R[(long long)t * n + j], acc);
+  A[(long long)i * n + j] = acc;
+}
+
+extern "C" long long pmb_dense_invert_ws_doubles(int n) { return (long long)GJB * GJB + 2LL * GJB * (n > 0 ? n : 0); }
 
 extern "C" int pmb_dense_invert(int n, double* dense, double* scratch, int* info, void* stream) {
   PMB_REQUIRE(n > 0 && dense && scratch && info, "pmb_dense_invert: invalid argument");
@@ -387,10 +428,15 @@ extern "C" int pmb_dense_invert(int n, double* dense, double* scratch, int* info
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return pmb_set_error("pmb_dense_invert: %s", cudaGetErrorString(e));
+  double* P = scratch;
+  double* R = scratch + GJB * GJB;
+  double* C = R + (long long)GJB * n;
   dim3 grid((n + 255) / 256, n);
-  for (int k = 0; k < n; ++k) {
-    gj_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, k, dense, scratch, scratch + n, info);
-    gj_update_kernel<<<grid, 256, 0, st>>>(n, k, dense, scratch, scratch + n);
+  for (int k0 = 0; k0 < n; k0 += GJB) {
+    const int bs = n - k0 < GJB ? n - k0 : GJB;
+    gj_pivot_block_kernel<<<1, GJB * GJB, 0, st>>>(n, k0, bs, dense, P, info);
+    gj_panels_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, k0, bs, dense, P, R, C);
+    gj_rank_update_kernel<<<grid, 256, 0, st>>>(n, k0, bs, dense, R, C);
   }
   PMB_CHECK_LAUNCH("pmb_dense_invert");
   return 0;

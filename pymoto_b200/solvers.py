@@ -119,7 +119,7 @@ class SolverDenseInverse(LinearSolver):
         if self.inv is None or self.n != n:
             self.n = n
             self.inv = dv.empty(n * n)
-            self._scratch = dv.empty(2 * n)
+            self._scratch = dv.empty(_lib.query("pmb_dense_invert_ws_doubles", n))
             self._info = dv.zeros(1, torch.int32)
             self._out = dv.empty(n)
         st = dv.stream()

@@ -186,7 +186,7 @@ def test_dense_inverse_and_vector_kernels(pmb):
     M = rng.standard_normal((n, n))
     M = M @ M.T + n * np.eye(n)
     Md = dv.to_device(M.ravel().copy())
-    scratch, info = dv.empty(2 * n), dv.zeros(1, torch.int32)
+    scratch, info = dv.empty(_lib.query("pmb_dense_invert_ws_doubles", n)), dv.zeros(1, torch.int32)
     _lib.call("pmb_dense_invert", n, dv.ptr(Md), dv.ptr(scratch), dv.ptr(info), dv.stream())
     assert int(info.item()) == 0
     np.testing.assert_allclose(Md.cpu().numpy().reshape(n, n), np.linalg.inv(M), rtol=0, atol=1e-12)
