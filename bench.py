@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="sample grid of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--csr", action="store_true", help="stream the assembled CSR values on every level (no matrix-free level 0)")
     ap.add_argument("--kernel-only", action="store_true", help="only the dominant-kernel loop (for ncu captures)")
     ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event breakdown of one step (diagnostic)")
     return ap.parse_args()
@@ -228,6 +229,10 @@ def run_b200(args, full):
     ge.build()
     from pymoto_b200 import _lib, device as dv
 
+    if args.csr:
+        from pymoto_b200.matrix import DeviceCSR as _D
+
+        _D.matrix_free = False
     chain = GpuChain(full, world)
     W, K = args.warmup, args.steps
     xs_host = design_sequence(chain.dom.nel, W + K + (1 if args.profile else 0), keep=chain.local)
@@ -319,24 +324,38 @@ def run_b200(args, full):
         e2e = {"value": dof_scale * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * nel * world,
                "d2h_bytes_per_step": (8 * nel + 8) * world}
 
-    # ---------------- roofline of the dominant kernel: fused Jacobi sweep on the finest level
+    # ---------------- roofline.  Two kernels carry the step:
+    #  (1) the HBM-bound stencil-CSR kernel (tile_kernel, fused Jacobi sweep): timed on the finest ASSEMBLED matrix
+    #      (the CSR values of level 0, 8*nnz bytes per sweep) -- this is `roofline`;
+    #  (2) with --matrix-free (default) level 0 is applied from the element densities instead (elem_kernel, FP64-pipe
+    #      bound, 0.46 GB per application): reported under `matrix_free` with the time the same application would
+    #      need at 100 % of the HBM peak if it streamed the assembled values.
+    from pymoto_b200.matrix import DeviceCSR
+
     A = chain.asm._mat
     n, nnz = A.shape[0], A.nnz
     mg0 = chain.mgs[0]
     u, u2, b = mg0._buf["u"], mg0._buf["u2"], mg0._buf["t"]
     D = mg0.smoother.D
-    reps = 20
-    for _ in range(3):
-        A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=0.5)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=0.5)
-        u, u2 = u2, u
-    k1.record()
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / reps
+
+    def time_sweeps(reps=20):
+        nonlocal u, u2
+        for _ in range(3):
+            A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=0.5)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            A.apply(_lib.JACOBI, u, u2, b=b, diag=D, w=0.5)
+            u, u2 = u2, u
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
+    was_mf = DeviceCSR.matrix_free
+    DeviceCSR.matrix_free = False
+    kern_ms = time_sweeps()
+    DeviceCSR.matrix_free = was_mf
     alg_bytes = 8 * nnz + 32 * n  # values once; x, b, diag read and y written once (Jacobi sweep)
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -344,15 +363,30 @@ def run_b200(args, full):
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    fine_calls = sum(v for (name, det), v in stats.items() if name == "pmb_spmv" and det[0] == full[0])
+    fine_csr = sum(v for (name, det), v in stats.items() if name == "pmb_spmv" and det[0] == full[0])
+    fine_mf = sum(v for (name, det), v in stats.items() if name == "pmb_elem_spmv" and det[0] == full[0])
+    csr_calls = sum(v for (name, det), v in stats.items() if name == "pmb_spmv")
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
     # (profiles/ncu_full_tile_kernel_r1b.txt: 8.5216 GB + 0.0906 GB per launch at 256x128x128)
     traffic = 8.5216e9 + 0.0906e9 if (tuple(full) == (256, 128, 128) and world == 1) else None
+    step_avg_ms = total_ms / K
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "tile_kernel<3,JACOBI> (finest level)", "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes,
-                "peak_source": peak_src, "reference_layout_gbs": (12 * nnz + 4 * (n + 1) + 40 * n) / (kern_ms * 1e-3) / 1e9,
-                "fine_level_operator_launches_per_step": fine_calls / K,
-                "share_of_step": fine_calls / K * kern_ms / (total_ms / K)}
+                "kernel": "tile_kernel<3,JACOBI> on the finest assembled matrix", "kernel_ms": kern_ms,
+                "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "reference_layout_gbs": (12 * nnz + 4 * (n + 1) + 40 * n) / (kern_ms * 1e-3) / 1e9,
+                "fine_level_operator_launches_per_step": (fine_csr + fine_mf) / K,
+                "stencil_csr_launches_per_step": csr_calls / K,
+                "share_of_step": (fine_csr / K) * kern_ms / step_avg_ms if not was_mf else None}
+    matrix_free = None
+    if was_mf:
+        mf_ms = time_sweeps()
+        flops = 2.0 * 600 * (n / 3)  # 8 elements x (72 + 3) FMA per node
+        matrix_free = {"kernel": "elem_kernel<3,3D,JACOBI> (finest level from element densities)", "kernel_ms": mf_ms,
+                       "bound": "fp64 pipe", "fp64_tflops": flops / (mf_ms * 1e-3) / 1e12, "dram_bytes_algorithmic": 40 * n + 8 * nel,
+                       "launches_per_step": fine_mf / K, "share_of_step": (fine_mf / K) * mf_ms / step_avg_ms,
+                       "speedup_vs_streaming_assembled_values": kern_ms / mf_ms,
+                       "assembled_layout_time_at_100pct_hbm_peak_ms": alg_bytes / (peak * 1e9) * 1e3,
+                       "step_ms_if_level0_streamed_at_100pct_hbm_peak": step_avg_ms + (fine_mf / K) * (alg_bytes / (peak * 1e9) * 1e3 - mf_ms)}
 
     # ---------------- CPU baseline (bounded sample), rank 0 only
     cpu = None
@@ -373,13 +407,15 @@ def run_b200(args, full):
             "config": {"workload": f"3D cantilever compliance {full[0]}x{full[1]}x{full[2]} hex8 ({chain.ndof_global} dof, "
                                    f"{n} dof / nnz {nnz} per GPU), "
                                    f"SIMP p=3 xmin=1e-9, DensityFilter r=2, LDAS+CG(tol 1e-8)+GMG({len(chain.mgs)} levels, "
-                                   "5+5 Jacobi w=0.5), warm start, seeded design perturbations",
+                                   "5+5 Jacobi w=0.5), warm start, seeded design perturbations; finest-level operator " +
+                                   ("matrix-free (element-wise)" if not args.csr else "streamed from the assembled CSR values"),
                        "l2": "inputs larger than L2 (matrix values 8*nnz bytes per level-0 sweep)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} z-slabs ({chain.ctx.part.n_dist} split multigrid levels, coarser levels replicated), NCCL halo "
                        "exchange + dot-product all-reduce; value = iterations/s x dof / 12.83M (weak scaling)",
                        "iters_per_sec_this_grid": iters_per_sec},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "matrix_free": matrix_free,
+            "cpu_baseline": cpu,
             "cg_iterations": cg_its, "ms_per_step_list": step_ms, "compliance": compl,
         }
         print(json.dumps(line))
