@@ -18,6 +18,8 @@
  *   pmb_dots / pmb_lincomb / pmb_cg_xr_update
  *                        pymoto/solvers/iterative.py:376-395  (CG dot products and vector updates)
  *   pmb_bc_split         pymoto/solvers/solvers.py:175-176    (Dirichlet dofs: u = f/diag, rhs zeroed)
+ *   pmb_pad_gather / pmb_stencil_corr / pmb_pad_scatter
+ *                        pymoto/modules/filter.py:182-220     (FilterConv: index-mapped padding, scipy.signal convolve/correlate)
  *   pmb_filter_apply / pmb_vec_div
  *                        pymoto/modules/filter.py:266-270     (csc_matvec of H, division by Hs)
  *
@@ -153,6 +155,17 @@ int pmb_mask_zero(long long n, const unsigned char* mask, const double* in, doub
  * point at layer ez0 and `in` is read d layers beyond on each side where those exist in the domain. */
 int pmb_filter_apply(const pmb_grid* g, int ez0, int nezl, int d, const double* wtab, const double* in,
                      const double* hs, double* out, void* stream);
+/* FilterConv (pymoto/modules/filter.py:8-220): padded convolution filter.
+ * pmb_pad_gather: xpad (pz,py,px; x fastest) from x (nz,ny,nx) through per-axis index maps (-1 = constant padding with the
+ * value cv*[index]; the outermost constant axis wins, z over y over x).  pmb_stencil_corr: out[o] = sum_q w[q] in[o+q-off]
+ * with `in` zero outside its extent.  pmb_pad_scatter: dx[s] = sum of dxpad over the padded positions mapping to s
+ * (per-axis inverse lists, CSR form: ptr (n+1), lst). */
+int pmb_pad_gather(int nx, int ny, int nz, int px, int py, int pz, const int* mapx, const int* mapy, const int* mapz,
+                   const double* cvx, const double* cvy, const double* cvz, const double* x, double* xpad, void* stream);
+int pmb_pad_scatter(int nx, int ny, int nz, int px, int py, int pz, const int* ptrx, const int* lstx, const int* ptry,
+                    const int* lsty, const int* ptrz, const int* lstz, const double* dxpad, double* dx, void* stream);
+int pmb_stencil_corr(int inx, int iny, int inz, const double* in, int ox, int oy, int oz, double* out, int kx, int ky, int kz,
+                     const double* w, int offx, int offy, int offz, void* stream);
 /* out = a / b */
 int pmb_vec_div(long long n, const double* a, const double* b, double* out, void* stream);
 

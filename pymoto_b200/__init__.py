@@ -15,7 +15,7 @@ from .domain import VoxelDomain, DomainDefinition
 from .matrix import DeviceCSR
 from .dyad import DeviceDyad
 from .assembly import AssembleGeneral, AssembleStiffness, AssemblePoisson
-from .filter import DensityFilter, Filter
+from .filter import DensityFilter, Filter, FilterConv
 from .linalg import LinSolve
 from .glue import SIMP, Compliance
 from . import solvers
@@ -23,5 +23,5 @@ from . import slab
 from ._lib import PmbError
 
 __all__ = ["Signal", "Module", "Network", "VoxelDomain", "DomainDefinition", "DeviceCSR", "DeviceDyad",
-           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "LinSolve", "SIMP", "Compliance", "solvers", "slab",
+           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "FilterConv", "LinSolve", "SIMP", "Compliance", "solvers", "slab",
            "PmbError", "HAVE_PYMOTO"]

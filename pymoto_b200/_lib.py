@@ -72,6 +72,9 @@ SIGNATURES = {
     "pmb_diag_mask": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_mask_zero": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_filter_apply": (_I, [_G, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pmb_pad_gather": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pmb_pad_scatter": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pmb_stencil_corr": (_I, [_I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
     "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),

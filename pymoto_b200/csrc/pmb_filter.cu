@@ -82,3 +82,112 @@ extern "C" int pmb_filter_apply(const pmb_grid* p, int ez0, int nezl, int d, con
   PMB_CHECK_LAUNCH("pmb_filter_apply");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------- FilterConv
+// Padded convolution filter of pymoto/modules/filter.py:8-220.  The reference materialises an index array el3d_pad
+// ((n+2p)^3 int64) and calls scipy.signal.convolve / correlate; here the padding is a separable per-axis index map
+// (symmetric / edge / wrap / constant, built on the host with the reference's own np.pad sequence), applied by a
+// gather kernel, and the convolution is a direct stencil.
+
+// xpad[pz][py][px] = constant of the outermost constant-padded axis (z wins over y over x, the order in which the
+// reference applies its overrides, filter.py:99-160,183-187), else x[(mz*ny + my)*nx + mx]
+__global__ void __launch_bounds__(256) pad_gather_kernel(int nx, int ny, int px, int py, int pz, const int* __restrict__ mapx,
+                                                          const int* __restrict__ mapy, const int* __restrict__ mapz,
+                                                          const double* __restrict__ cvx, const double* __restrict__ cvy,
+                                                          const double* __restrict__ cvz, const double* __restrict__ x,
+                                                          double* __restrict__ xpad) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)px * py * pz;
+  if (t >= n) return;
+  int ix = (int)(t % px), iy = (int)((t / px) % py), iz = (int)(t / ((long long)px * py));
+  int mx = mapx[ix], my = mapy[iy], mz = mapz[iz];
+  double v;
+  if (mz < 0) v = cvz[iz];
+  else if (my < 0) v = cvy[iy];
+  else if (mx < 0) v = cvx[ix];
+  else v = x[((long long)mz * ny + my) * nx + mx];
+  xpad[t] = v;
+}
+
+extern "C" int pmb_pad_gather(int nx, int ny, int nz, int px, int py, int pz, const int* mapx, const int* mapy, const int* mapz,
+                              const double* cvx, const double* cvy, const double* cvz, const double* x, double* xpad,
+                              void* stream) {
+  PMB_REQUIRE(nx > 0 && ny > 0 && nz > 0 && px > 0 && py > 0 && pz > 0, "pmb_pad_gather: invalid sizes");
+  PMB_REQUIRE(mapx && mapy && mapz && cvx && cvy && cvz && x && xpad, "pmb_pad_gather: NULL pointer argument");
+  long long n = (long long)px * py * pz;
+  pad_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nx, ny, px, py, pz, mapx, mapy, mapz, cvx, cvy,
+                                                                                     cvz, x, xpad);
+  PMB_CHECK_LAUNCH("pmb_pad_gather");
+  return 0;
+}
+
+// dx[s] = sum over the padded positions that map to s (per-axis inverse lists in CSR form) of dxpad
+__global__ void __launch_bounds__(256) pad_scatter_kernel(int nx, int ny, int nz, int px, int py, const int* __restrict__ ptrx,
+                                                           const int* __restrict__ lstx, const int* __restrict__ ptry,
+                                                           const int* __restrict__ lsty, const int* __restrict__ ptrz,
+                                                           const int* __restrict__ lstz, const double* __restrict__ dxpad,
+                                                           double* __restrict__ dx) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)nx * ny * nz;
+  if (t >= n) return;
+  int ix = (int)(t % nx), iy = (int)((t / nx) % ny), iz = (int)(t / ((long long)nx * ny));
+  double acc = 0.0;
+  for (int a = ptrz[iz]; a < ptrz[iz + 1]; ++a)
+    for (int b = ptry[iy]; b < ptry[iy + 1]; ++b)
+      for (int c = ptrx[ix]; c < ptrx[ix + 1]; ++c) acc += dxpad[((long long)lstz[a] * py + lsty[b]) * px + lstx[c]];
+  dx[t] = acc;
+}
+
+extern "C" int pmb_pad_scatter(int nx, int ny, int nz, int px, int py, int pz, const int* ptrx, const int* lstx, const int* ptry,
+                               const int* lsty, const int* ptrz, const int* lstz, const double* dxpad, double* dx, void* stream) {
+  PMB_REQUIRE(nx > 0 && ny > 0 && nz > 0 && px > 0 && py > 0 && pz > 0, "pmb_pad_scatter: invalid sizes");
+  PMB_REQUIRE(ptrx && lstx && ptry && lsty && ptrz && lstz && dxpad && dx, "pmb_pad_scatter: NULL pointer argument");
+  long long n = (long long)nx * ny * nz;
+  pad_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nx, ny, nz, px, py, ptrx, lstx, ptry, lsty, ptrz,
+                                                                                     lstz, dxpad, dx);
+  PMB_CHECK_LAUNCH("pmb_pad_scatter");
+  return 0;
+}
+
+// out[o] = sum_q w[q] in[o + q - off]  (per axis), `in` taken as zero outside its extent.  Forward filter: in = padded
+// field, off = 0, w = flipped weights ("valid" convolution); backward: in = dy, off = K-1, w = weights ("full" correlation).
+__global__ void __launch_bounds__(256) stencil_corr_kernel(int inx, int iny, int inz, const double* __restrict__ in, int ox, int oy,
+                                                            int oz, double* __restrict__ out, int kx, int ky, int kz,
+                                                            const double* __restrict__ w, int offx, int offy, int offz) {
+  extern __shared__ double sw[];
+  for (int q = threadIdx.x; q < kx * ky * kz; q += blockDim.x) sw[q] = w[q];
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)ox * oy * oz;
+  if (t >= n) return;
+  int x = (int)(t % ox), y = (int)((t / ox) % oy), z = (int)(t / ((long long)ox * oy));
+  double acc = 0.0;
+  for (int c = 0; c < kz; ++c) {
+    int zz = z + c - offz;
+    if (zz < 0 || zz >= inz) continue;
+    for (int b = 0; b < ky; ++b) {
+      int yy = y + b - offy;
+      if (yy < 0 || yy >= iny) continue;
+      const double* row = in + ((long long)zz * iny + yy) * inx;
+      const double* wr = sw + (c * ky + b) * kx;
+      for (int a = 0; a < kx; ++a) {
+        int xx = x + a - offx;
+        if (xx >= 0 && xx < inx) acc = fma(wr[a], __ldg(row + xx), acc);
+      }
+    }
+  }
+  out[t] = acc;
+}
+
+extern "C" int pmb_stencil_corr(int inx, int iny, int inz, const double* in, int ox, int oy, int oz, double* out, int kx, int ky,
+                                int kz, const double* w, int offx, int offy, int offz, void* stream) {
+  PMB_REQUIRE(inx > 0 && iny > 0 && inz > 0 && ox > 0 && oy > 0 && oz > 0 && kx > 0 && ky > 0 && kz > 0, "pmb_stencil_corr: invalid sizes");
+  PMB_REQUIRE(in && out && w, "pmb_stencil_corr: NULL pointer argument");
+  size_t smem = sizeof(double) * kx * ky * kz;
+  PMB_REQUIRE(smem <= 48 * 1024, "pmb_stencil_corr: kernel of %d x %d x %d weights too large", kx, ky, kz);
+  long long n = (long long)ox * oy * oz;
+  stencil_corr_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(inx, iny, inz, in, ox, oy, oz, out, kx, ky, kz, w,
+                                                                                         offx, offy, offz);
+  PMB_CHECK_LAUNCH("pmb_stencil_corr");
+  return 0;
+}

@@ -82,3 +82,158 @@ class DensityFilter(Module):
 
 
 Filter = DensityFilter
+
+
+class FilterConv(Module):
+    r"""Density filter as a padded convolution, :math:`y = W \ast x` (pymoto/modules/filter.py:8-220).
+
+    Same constructor as the reference: either ``radius`` (cone kernel, normalised to unit sum) or explicit ``weights``;
+    per-face boundary treatment ``"symmetric"`` (default), ``"edge"``, ``"wrap"`` or a constant value.  The padded
+    index array of the reference is replaced by per-axis index maps (built with the same ``np.pad`` sequence) and
+    the convolution by a direct stencil on the GPU; ``override_values`` / ``override_padded_values`` are kept.
+    """
+
+    def __init__(self, domain, radius: float = None, relative_units: bool = True, weights=None, xmin_bc="symmetric",
+                 xmax_bc="symmetric", ymin_bc="symmetric", ymax_bc="symmetric", zmin_bc="symmetric", zmax_bc="symmetric"):
+        dv.require_cuda()
+        if slab.context().active:
+            raise NotImplementedError("FilterConv is single-GPU in this build; use DensityFilter for slab-decomposed runs")
+        self.domain = domain
+        self.weights = None
+        if (weights is None and radius is None) or (weights is not None and radius is not None):
+            raise ValueError("Only one of arguments 'filter_radius' or 'weights' must be provided.")
+        elif weights is not None:
+            self.weights = np.array(weights, dtype=float)
+            while self.weights.ndim < 3:
+                self.weights = np.expand_dims(self.weights, axis=-1)
+            for i in range(self.weights.ndim):
+                assert self.weights.shape[i] % 2 == 1, "Size of weights must be uneven"
+        else:
+            self.set_filter_radius(radius, relative_units)
+        nx, ny, nz = grid_dims(domain)
+        self._n = (nx, ny, max(nz, 1))
+        self.nel = nx * ny * max(nz, 1)
+        self.pad_sizes = [v // 2 for v in self.weights.shape]
+        self._p = tuple(n + 2 * p for n, p in zip(self._n, self.pad_sizes))
+        self.overrides = []  # user overrides: (flat padded indices (device int64), value)
+        maps = [self._axis_map(self._n[a], self.pad_sizes[a], bc0, bc1)
+                for a, (bc0, bc1) in enumerate([(xmin_bc, xmax_bc), (ymin_bc, ymax_bc), (zmin_bc, zmax_bc)])]
+        self._map = [dv.to_device(m[0].astype(np.int32), torch.int32) for m in maps]
+        self._cval = [dv.to_device(m[1]) for m in maps]
+        # inverse maps (which padded positions read a given source index), CSR form, for the backward scatter
+        self._inv = []
+        for m, _ in maps:
+            order = np.argsort(m, kind="stable")
+            order = order[m[order] >= 0]
+            counts = np.bincount(m[m >= 0], minlength=0)
+            ptr = np.zeros(len(counts) + 1, dtype=np.int32)
+            np.cumsum(counts, out=ptr[1:])
+            self._inv.append((dv.to_device(ptr, torch.int32), dv.to_device(order.astype(np.int32), torch.int32)))
+        self._upload_weights()
+
+    def _upload_weights(self):
+        w = np.ascontiguousarray(self.weights, dtype=np.float64)
+        # device layout is (z, y, x) with x fastest; scipy's convolve flips the kernel, correlate does not
+        self._w_bwd = dv.to_device(np.ascontiguousarray(w.transpose(2, 1, 0)).ravel())
+        self._w_fwd = dv.to_device(np.ascontiguousarray(w[::-1, ::-1, ::-1].transpose(2, 1, 0)).ravel())
+
+    @staticmethod
+    def _axis_map(n, pad, bc0, bc1):
+        """Source index of every padded position along one axis (-1 = constant padding) and the constant values;
+        the reference's sequence: wrap sides first, then the max edge, then the min edge (filter.py:99-160)."""
+        from numbers import Number
+
+        idx = np.arange(n)
+        cval = np.zeros(n + 2 * pad)
+        if pad == 0:
+            return idx, cval
+        wrap = (pad if bc0 == "wrap" else 0, pad if bc1 == "wrap" else 0)
+        a = np.pad(idx, wrap, mode="wrap") if (wrap[0] or wrap[1]) else idx
+        if bc1 == "edge":
+            a = np.pad(a, (0, pad), mode="edge")
+        elif bc1 == "symmetric":
+            a = np.pad(a, (0, pad), mode="symmetric")
+        elif isinstance(bc1, Number):
+            a = np.pad(a, (0, pad), mode="constant", constant_values=-1)
+            cval[pad + n:] = bc1
+        elif bc1 != "wrap":
+            raise ValueError(f"Unknown boundary condition {bc1!r}")
+        if bc0 == "edge":
+            a = np.pad(a, (pad, 0), mode="edge")
+        elif bc0 == "symmetric":
+            a = np.pad(a, (pad, 0), mode="symmetric")
+        elif isinstance(bc0, Number):
+            a = np.pad(a, (pad, 0), mode="constant", constant_values=-1)
+            cval[:pad] = bc0
+        elif bc0 != "wrap":
+            raise ValueError(f"Unknown boundary condition {bc0!r}")
+        assert a.size == n + 2 * pad
+        return a, cval
+
+    def set_filter_radius(self, radius: float, relative_units: bool = True):
+        """Cone kernel max(0, r - dist), normalised (filter.py:189-205)."""
+        if relative_units:
+            dx, dy, dz = 1.0, 1.0, 1.0
+        else:
+            dx, dy, dz = self.domain.element_size
+        nx, ny, nz = grid_dims(self.domain)
+        delemx = min(nx, int((radius - 1e-10 * dx) / dx))
+        delemy = min(ny, int((radius - 1e-10 * dy) / dy))
+        delemz = min(nz, int((radius - 1e-10 * dz) / dz))
+        cx, cy, cz = np.meshgrid(np.arange(-delemx, delemx + 1) * dx, np.arange(-delemy, delemy + 1) * dy,
+                                 np.arange(-delemz, delemz + 1) * dz, indexing="ij")
+        self.weights = np.maximum(0.0, radius - np.sqrt(cx * cx + cy * cy + cz * cz))
+        self.weights /= np.sum(self.weights)  # volume preserving
+        if hasattr(self, "_w_fwd"):
+            self._upload_weights()
+
+    # ---- user overrides of padded / domain values (filter.py:167-180)
+    def override_padded_values(self, index, value):
+        ix, iy, iz = (np.asarray(i) for i in index)
+        if ix.size == 0:
+            return
+        flat = (np.broadcast_arrays(ix, iy, iz)[2] * self._p[1] + np.broadcast_arrays(ix, iy, iz)[1]) * self._p[0] \
+            + np.broadcast_arrays(ix, iy, iz)[0]
+        self.overrides.append((dv.to_device(flat.ravel().astype(np.int64), torch.int64), float(value)))
+
+    def override_values(self, index, value):
+        xr = self.pad_sizes[0] + np.arange(self._n[0])
+        yr = self.pad_sizes[1] + np.arange(self._n[1])
+        zr = self.pad_sizes[2] + np.arange(self._n[2])
+        ex, ey, ez = np.meshgrid(xr, yr, zr, indexing="ij")
+        self.override_padded_values((ex[index], ey[index], ez[index]), value)
+
+    def get_padded_vector(self, x):
+        """Padded field on the device, flat in (z, y, x) order with x fastest."""
+        xd = dv.to_device(x).reshape(-1)
+        xpad = dv.empty(self._p[0] * self._p[1] * self._p[2])
+        _lib.call("pmb_pad_gather", *self._n, *self._p, dv.ptr(self._map[0]), dv.ptr(self._map[1]), dv.ptr(self._map[2]),
+                  dv.ptr(self._cval[0]), dv.ptr(self._cval[1]), dv.ptr(self._cval[2]), dv.ptr(xd), dv.ptr(xpad), dv.stream())
+        for idx, value in self.overrides:
+            xpad[idx] = value
+        return xpad
+
+    def __call__(self, x):
+        n = x.numel() if isinstance(x, torch.Tensor) else np.size(x)
+        if n != self.nel:
+            raise ValueError(f"Input vector wrong size ({n}), must be equal to #nel ({self.nel})")
+        xpad = self.get_padded_vector(x)
+        y = dv.empty(self.nel)
+        k = self.weights.shape
+        _lib.call("pmb_stencil_corr", *self._p, dv.ptr(xpad), *self._n, dv.ptr(y), k[0], k[1], k[2], dv.ptr(self._w_fwd),
+                  0, 0, 0, dv.stream())
+        return dv.like_input(y, x)
+
+    def _sensitivity(self, dfdv):
+        dy = dv.to_device(dfdv).reshape(-1)
+        k = self.weights.shape
+        dxpad = dv.empty(self._p[0] * self._p[1] * self._p[2])
+        _lib.call("pmb_stencil_corr", *self._n, dv.ptr(dy), *self._p, dv.ptr(dxpad), k[0], k[1], k[2], dv.ptr(self._w_bwd),
+                  k[0] - 1, k[1] - 1, k[2] - 1, dv.stream())
+        for idx, _ in self.overrides:
+            dxpad[idx] = 0.0
+        dx = dv.empty(self.nel)
+        _lib.call("pmb_pad_scatter", *self._n, *self._p, dv.ptr(self._inv[0][0]), dv.ptr(self._inv[0][1]),
+                  dv.ptr(self._inv[1][0]), dv.ptr(self._inv[1][1]), dv.ptr(self._inv[2][0]), dv.ptr(self._inv[2][1]),
+                  dv.ptr(dxpad), dv.ptr(dx), dv.stream())
+        return dv.like_input(dx, dfdv)

@@ -165,7 +165,50 @@ def jacobi_cg_case():
     print("jacobi cg relres", np.linalg.norm(K @ u - fl) / np.linalg.norm(fl))
 
 
+FILTERCONV_CASES = [
+    # name, shape, kwargs (weights given as a seed -> random asymmetric kernel of that shape)
+    ("sym3d", (7, 5, 4), dict(radius=2.0)),
+    ("r3_3d", (9, 6, 5), dict(radius=3.2)),
+    ("sym2d", (12, 9, 0), dict(radius=2.5)),
+    ("edge_wrap", (8, 6, 5), dict(radius=2.0, xmin_bc="edge", xmax_bc="wrap", ymin_bc="wrap", ymax_bc="wrap", zmin_bc="edge", zmax_bc="edge")),
+    ("const", (6, 7, 5), dict(radius=2.0, xmin_bc=0.0, xmax_bc=1.0, ymin_bc=0.25, ymax_bc="symmetric", zmin_bc="edge", zmax_bc=0.75)),
+    ("weights", (6, 5, 4), dict(weights_shape=(3, 5, 3), xmin_bc="wrap", xmax_bc="symmetric", ymin_bc=0.5, ymax_bc="edge")),
+    ("weights2d", (9, 8, 0), dict(weights_shape=(5, 3), xmin_bc="edge", ymax_bc=2.0)),
+    ("override", (6, 6, 4), dict(radius=2.0, override=True)),
+]
+
+
+def filterconv_case():
+    """FilterConv forward / backward for every boundary mode (reference tests/test_filter.py:13-223 pin these by impulse
+    responses and finite differences; here the reference's outputs themselves are stored)."""
+    out = {}
+    for name, shape, kw in FILTERCONV_CASES:
+        kw = dict(kw)
+        d = pym.VoxelDomain(*shape)
+        rng = np.random.default_rng(len(name) * 7 + shape[0])
+        wshape = kw.pop("weights_shape", None)
+        override = kw.pop("override", False)
+        if wshape is not None:
+            kw["weights"] = np.random.default_rng(len(name)).random(wshape)
+            out[name + "_weights"] = kw["weights"]
+        m = pym.FilterConv(d, **kw)
+        if override:
+            m.override_values((np.s_[1:3], np.s_[2:4], np.s_[:]), 1.0)  # a fixed solid region inside the domain
+        x = rng.random(d.nel)
+        dy = rng.standard_normal(d.nel)
+        sx = pym.Signal("x", state=x)
+        sy = m(sx)
+        sy.sensitivity = dy
+        m.sensitivity()
+        out[name + "_x"], out[name + "_y"], out[name + "_dy"], out[name + "_dx"] = x, sy.state, dy, sx.sensitivity
+        print(f"filterconv {name}: weights {m.weights.shape}, |y| {np.linalg.norm(sy.state):.6f}")
+    np.savez_compressed(os.path.join(HERE, "ref_filterconv.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "filterconv":
+        filterconv_case()
+        sys.exit(0)
     run_case("hex_6x4x4", "cantilever", 6, 4, 4, min_size=8, store_matrix=True)
     run_case("quad_12x8", "cantilever", 12, 8, 0, min_size=4, store_matrix=True)
     run_case("hex_16x8x8", "cantilever", 16, 8, 8, min_size=4, store_matrix=False)
@@ -173,3 +216,4 @@ if __name__ == "__main__":
     run_case("mbb_8x4x4", "mbb3d", 8, 4, 4, min_size=4, store_matrix=False)
     transfer_case()
     jacobi_cg_case()
+    filterconv_case()
