@@ -221,6 +221,10 @@ def run_b200(args, full):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout for the ONE JSON line: anything libraries print (e.g. the NCCL version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -418,7 +422,9 @@ def run_b200(args, full):
             "cpu_baseline": cpu,
             "cg_iterations": cg_its, "ms_per_step_list": step_ms, "compliance": compl,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
