@@ -23,7 +23,7 @@ struct KeParam {
 };
 
 template <int NDOF, bool DIM3, int MODE>
-__global__ void __launch_bounds__(256) elem_kernel(Geo g, const __grid_constant__ KeParam<NDOF, DIM3> ke, const double* __restrict__ s,
+__global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_constant__ KeParam<NDOF, DIM3> ke, const double* __restrict__ s,
                                                     const unsigned char* __restrict__ mask, double bcdiag,
                                                     const double* __restrict__ x, const double* __restrict__ b,
                                                     const double* __restrict__ diag, double w, double* __restrict__ y,
