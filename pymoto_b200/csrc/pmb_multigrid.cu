@@ -94,19 +94,31 @@ extern "C" int pmb_prolong_add(const pmb_grid* pf, const pmb_grid* pc, const dou
 template <int NDOF>
 struct GalCfg;
 template <>
-struct GalCfg<3> { static constexpr int T = 16, STAGES = 3; };
+struct GalCfg<3> { static constexpr int T = 16, STAGES = 2; };
 template <>
-struct GalCfg<2> { static constexpr int T = 48, STAGES = 2; };
+struct GalCfg<2> { static constexpr int T = 32, STAGES = 2; };
 template <>
-struct GalCfg<1> { static constexpr int T = 96, STAGES = 3; };
+struct GalCfg<1> { static constexpr int T = 96, STAGES = 2; };
 static constexpr int GAL_NT = 256;
 
+// trilinear weight of fine index p in the support of coarse index C (0 outside): 1 at p = 2C, 1/2 at 2C +- 1
+__device__ __forceinline__ double prolong_w(int p, int C) {
+  const int t = p - 2 * C;
+  return t == 0 ? 1.0 : ((t == 1 || t == -1) ? 0.5 : 0.0);
+}
+
+// Pass 1 is separable: the 27 fine neighbour blocks of a node are collapsed onto its 27 coarse slots one dimension
+// at a time (x, then y, then z), each step a uniform 3-term combination -> no divergent trip counts.
 template <int NDOF>
 __global__ void __launch_bounds__(GAL_NT, 2) galerkin_cols_kernel(Geo gf, Geo gc, int ntiles, int tiles_per_row, int stream_hint,
                                                                   const double* __restrict__ Af, double* __restrict__ B) {
   constexpr int T = GalCfg<NDOF>::T, STAGES = GalCfg<NDOF>::STAGES;
   constexpr int TD = (T * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
-  extern __shared__ __align__(128) double sTiles[];
+  constexpr int NB = NDOF * NDOF;      // doubles per block
+  constexpr int PB = 27 * NB;          // padded doubles per node in the intermediates
+  extern __shared__ __align__(128) double sTiles[];   // STAGES x TD ring, then one T x PB intermediate
+  double* s1 = sTiles + (size_t)STAGES * TD;
+  static_assert(TD >= T * PB, "the ring slot doubles as the second intermediate");
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   const int tid = threadIdx.x;
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -132,51 +144,88 @@ __global__ void __launch_bounds__(GAL_NT, 2) galerkin_cols_kernel(Geo gf, Geo gc
     const TileGeom t = tile_geom<NDOF, T>(gf, (int)blockIdx.x + it * (int)gridDim.x, tiles_per_row);
     const long long lnode0 = ((long long)(t.k - gf.kz0) * gf.NY + t.j) * gf.NX + t.i0;
     const double* tile = sTiles + (size_t)s * TD + (t.e0 - (t.e0 & ~1LL));
-    const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
+    const long long per = (long long)NB * t.cy * t.cz;
+    const int fj = t.j, fk = t.k;
+    double* s2 = sTiles + (size_t)s * TD;  // overwrites the staged values once the x-pass has consumed them
     mbar_wait(&full_bar[s], (unsigned)((it / STAGES) & 1));
 
+    // ---- x: s1[g][ez][ey][sx] = sum_ex w_x A[g][(ez,ey,ex)]
     for (int p = tid; p < t.ni * 27; p += GAL_NT) {
-      const int gI = p / 27, slot = p - gI * 27;
-      const int sk = slot / 9, sj = (slot / 3) % 3, si = slot % 3;
-      const int fi = t.i0 + gI, fj = t.j, fk = t.k;
-      const int Ci = (fi >> 1) + si - 1, Cj = (fj >> 1) + sj - 1, Ck = (fk >> 1) + sk - 1;
-      const bool valid = ((fi & 1) == 0 || si >= 1) && ((fj & 1) == 0 || sj >= 1) && ((fk & 1) == 0 || sk >= 1) && Ci >= 0 &&
-                         Ci < gc.NX && Cj >= 0 && Cj < gc.NY && Ck >= 0 && Ck < gc.NZ;
-      if (!valid) continue;
-      const int cx = cnt1(fi, gf.NX), ilo = max(fi - 1, 0);
-      const int L = cx * t.cy * t.cz * NDOF;
-      const double* nodep = tile + per * (pre1(fi, gf.NX) - pre1(t.i0, gf.NX));
-      double acc[NDOF][NDOF];
+      const int g = p / 27, q = p - g * 27;
+      const int ez = q / 9, ey = (q / 3) % 3, sx = q % 3;
+      const int fi = t.i0 + g;
+      const int pk = fk + ez - 1, pj = fj + ey - 1;
+      double acc[NB];
 #pragma unroll
-      for (int a = 0; a < NDOF; ++a)
+      for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+      if (pk >= 0 && pk < gf.NZ && pj >= 0 && pj < gf.NY) {
+        const int cx = cnt1(fi, gf.NX), ilo = max(fi - 1, 0);
+        const int L = cx * t.cy * t.cz * NDOF;
+        const double* nodep = tile + per * (pre1(fi, gf.NX) - pre1(t.i0, gf.NX));
+        const int Cx = (fi >> 1) + sx - 1;
+        const int rowb = ((pk - t.klo) * t.cy + (pj - t.jlo)) * cx;
 #pragma unroll
-        for (int c = 0; c < NDOF; ++c) acc[a][c] = 0.0;
-      for (int pk = max(fk - 1, 0); pk <= min(fk + 1, gf.NZ - 1); ++pk) {
-        const int tz = pk - 2 * Ck;
-        if (tz < -1 || tz > 1) continue;
-        for (int pj = max(fj - 1, 0); pj <= min(fj + 1, gf.NY - 1); ++pj) {
-          const int ty = pj - 2 * Cj;
-          if (ty < -1 || ty > 1) continue;
-          const double wzy = (tz ? 0.5 : 1.0) * (ty ? 0.5 : 1.0);
-          for (int pi = ilo; pi <= min(fi + 1, gf.NX - 1); ++pi) {
-            const int tx = pi - 2 * Ci;
-            if (tx < -1 || tx > 1) continue;
-            const double w = wzy * (tx ? 0.5 : 1.0);
-            const int nbr = ((pk - t.klo) * t.cy + (pj - t.jlo)) * cx + (pi - ilo);
-            const double* ap = nodep + nbr * NDOF;
+        for (int ex = -1; ex <= 1; ++ex) {
+          const int pi = fi + ex;
+          const double w = (pi >= 0 && pi < gf.NX && Cx >= 0 && Cx < gc.NX) ? prolong_w(pi, Cx) : 0.0;
+          if (w != 0.0) {
+            const double* ap = nodep + (rowb + (pi - ilo)) * NDOF;
 #pragma unroll
             for (int a = 0; a < NDOF; ++a)
 #pragma unroll
-              for (int c = 0; c < NDOF; ++c) acc[a][c] = fma(w, ap[a * L + c], acc[a][c]);
+              for (int c = 0; c < NDOF; ++c) acc[a * NDOF + c] = fma(w, ap[a * L + c], acc[a * NDOF + c]);
           }
         }
       }
-      // B layout [fine node][NDOF*NDOF][27 slots]: consecutive threads (slots) store consecutive doubles
-      double* bp = B + (lnode0 + gI) * (27 * NDOF * NDOF) + slot;
+      double* o = s1 + (size_t)g * PB + q * NB;
 #pragma unroll
-      for (int a = 0; a < NDOF; ++a)
+      for (int c = 0; c < NB; ++c) o[c] = acc[c];
+    }
+    __syncthreads();
+    // ---- y: s2[g][ez][sy][sx] = sum_ey w_y s1[g][ez][ey][sx]       (weights uniform over the tile)
+    for (int p = tid; p < t.ni * 27; p += GAL_NT) {
+      const int g = p / 27, q = p - g * 27;
+      const int ez = q / 9, sy = (q / 3) % 3, sx = q % 3;
+      const int Cy = (fj >> 1) + sy - 1;
+      double acc[NB];
 #pragma unroll
-        for (int c = 0; c < NDOF; ++c) bp[(a * NDOF + c) * 27] = acc[a][c];
+      for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int ey = 0; ey < 3; ++ey) {
+        const int pj = fj + ey - 1;
+        const double w = (pj >= 0 && pj < gf.NY && Cy >= 0 && Cy < gc.NY) ? prolong_w(pj, Cy) : 0.0;
+        const double* ip = s1 + (size_t)g * PB + ((ez * 3 + ey) * 3 + sx) * NB;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] = fma(w, ip[c], acc[c]);
+      }
+      double* o = s2 + (size_t)g * PB + q * NB;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) o[c] = acc[c];
+    }
+    __syncthreads();
+    // ---- z: B[g][sz][sy][sx] = sum_ez w_z s2[g][ez][sy][sx]  -> global, layout [fine node][NB][27 slots]
+    for (int p = tid; p < t.ni * 27; p += GAL_NT) {
+      const int g = p / 27, q = p - g * 27;
+      const int sz = q / 9, sy = (q / 3) % 3, sx = q % 3;
+      const int fi = t.i0 + g;
+      const int Cx = (fi >> 1) + sx - 1, Cy = (fj >> 1) + sy - 1, Cz = (fk >> 1) + sz - 1;
+      const bool valid = ((fi & 1) == 0 || sx >= 1) && ((fj & 1) == 0 || sy >= 1) && ((fk & 1) == 0 || sz >= 1) && Cx >= 0 &&
+                         Cx < gc.NX && Cy >= 0 && Cy < gc.NY && Cz >= 0 && Cz < gc.NZ;
+      if (!valid) continue;
+      double acc[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int ez = 0; ez < 3; ++ez) {
+        const int pk = fk + ez - 1;
+        const double w = (pk >= 0 && pk < gf.NZ) ? prolong_w(pk, Cz) : 0.0;
+        const double* ip = s2 + (size_t)g * PB + ((ez * 3 + sy) * 3 + sx) * NB;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[c] = fma(w, ip[c], acc[c]);
+      }
+      double* bp = B + (lnode0 + g) * (27 * NB) + q;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) bp[c * 27] = acc[c];
     }
     __syncthreads();
     if (tid == 0 && it + STAGES < my_tiles) {
@@ -245,7 +294,7 @@ template <int NDOF>
 static int launch_galerkin_cols(const Geo& gf, const Geo& gc, const double* Af, double* B, cudaStream_t st) {
   constexpr int T = GalCfg<NDOF>::T, STAGES = GalCfg<NDOF>::STAGES;
   constexpr int TD = (T * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
-  const size_t smem = sizeof(double) * TD * STAGES;
+  const size_t smem = sizeof(double) * ((size_t)TD * STAGES + (size_t)T * 27 * NDOF * NDOF);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(galerkin_cols_kernel<NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
