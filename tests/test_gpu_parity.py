@@ -485,3 +485,146 @@ def test_filterconv_vs_reference_golden(pmb, name):
         np.testing.assert_allclose(one, 1.0, rtol=1e-13)
     with pytest.raises(ValueError):
         pmb.FilterConv(pmb.VoxelDomain(4, 4, 4))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs
+def test_config0_mbb_2d_100x50(pmb):
+    """BASELINE.json configs[0]: 2-D MBB beam 100x50 quad4, x = 0.5, DensityFilter r=2, SIMP p=3.  The reference (scipy
+    direct solve) gives compliance 369.30859599959234; here through CG + one multigrid level."""
+    nx, ny = 100, 50
+    dom = pmb.VoxelDomain(nx, ny)
+    nodes = dom.nodes
+    bc = np.concatenate([2 * nodes[0, :].flatten(), 2 * nodes[nx, 0].flatten() + 1])  # u_x = 0 on i = 0, u_y = 0 at (nx, 0)
+    f = np.zeros(dom.nnodes * 2)
+    f[2 * nodes[0, ny].flatten() + 1] = -1.0
+    x = np.full(dom.nel, 0.5)
+    y = pmb.DensityFilter(dom, radius=2.0)(x)
+    s = 1e-9 + (1.0 - 1e-9) * y ** 3
+    K = pmb.AssembleStiffness(dom, bc=bc)(s)
+    mgs = pmb.solvers.auto_multigrid(dom)
+    cg = pmb.solvers.CG(preconditioner=mgs[0], tol=1e-10)
+    u = pmb.LinSolve(hermitian=True, solver=cg)(K, f)
+    c = float(u @ f)
+    assert abs(c - 369.30859599959234) <= 1e-6 * 369.30859599959234
+    Ks = K.tocsr()
+    assert np.linalg.norm(Ks @ u - f) / np.linalg.norm(f) <= 1e-8
+    # the same system solved directly by the oracle's sparse LU
+    import scipy.sparse.linalg as spla
+
+    uref = spla.spsolve(Ks.tocsc(), f)
+    np.testing.assert_allclose(u, uref, rtol=0, atol=1e-7 * np.abs(uref).max())
+
+
+def test_config4_thermal_chain_vs_oracle(pmb):
+    """BASELINE.json configs[4] (heat-sink, scalar conduction, AssemblePoisson) at 32^3 against the CPU oracle."""
+    nx = ny = nz = 32
+    P = ComplianceProblem(Grid(nx, ny, nz), kind="heatsink", tol=1e-8, min_size=8)
+    x = np.random.default_rng(8).random(P.grid.nel) * 0.8 + 0.2
+    c_ref = P.response(x)
+    dx_ref = P.sensitivity()
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    flt = pmb.DensityFilter(dom, radius=2.0)
+    y = flt(x)
+    assert np.array_equal(y, P.y)
+    s = 1e-9 + (1.0 - 1e-9) * y ** 3
+    asm = pmb.AssemblePoisson(dom, bc=P.bc)
+    K = asm(s)
+    assert np.array_equal(K.data.cpu().numpy(), P.K.data)
+    mgs = pmb.solvers.auto_multigrid(dom, min_size=8)
+    assert len(mgs) == len(P.mgs)
+    cg = pmb.solvers.CG(preconditioner=mgs[0], tol=1e-8)
+    ls = pmb.LinSolve(hermitian=True, solver=cg)
+    u = ls(K, P.f)
+    c = float(u @ P.f)
+    assert abs(c - c_ref) <= 1e-6 * abs(c_ref)
+    assert abs(cg.iterations - P.cg.iterations) <= 1
+    dmat, _ = ls._sensitivity(P.f)
+    ds = asm._sensitivity(dmat)[0]
+    dx = flt._sensitivity(ds * (3.0 * (1.0 - 1e-9) * y ** 2))
+    np.testing.assert_allclose(dx, dx_ref, rtol=1e-6, atol=1e-7 * np.abs(dx_ref).max())
+
+
+def test_full_size_properties_256x128x128(pmb):
+    """Size-independent properties at BASELINE's full size (12.8 M dof, too big for the CPU oracle):
+    rigid-body translations lie in the null space of the unconstrained operator, the operator is symmetric, a constant
+    field passes the filter unchanged, the matrix-free and the assembled operator agree, and the solve reaches 1e-8."""
+    import torch
+    from pymoto_b200 import _lib, device as dv
+    from pymoto_b200.matrix import DeviceCSR
+
+    nx, ny, nz = 256, 128, 128
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    rng = np.random.default_rng(0)
+    xe = dv.to_device(rng.random(dom.nel) * 0.9 + 0.1)
+    flt = pmb.DensityFilter(dom, radius=2.0)
+    ones = dv.to_device(np.ones(dom.nel))
+    assert torch.allclose(flt(ones), ones, rtol=1e-14, atol=0)  # (H 1)/Hs = 1
+    # linearity of the filter transpose pair: <H x, y> = <x, H^T y>
+    a, b = flt(xe), flt._sensitivity(xe)
+    assert abs(float(a @ xe) - float(xe @ b)) <= 1e-10 * abs(float(a @ xe))
+    # unconstrained stiffness: K * (rigid translation) = 0, row sums of the values vanish
+    K0 = pmb.AssembleStiffness(dom)(xe)
+    n = K0.shape[0]
+    t = dv.zeros(n)
+    t[2::3] = 1.0
+    for mf in (True, False):
+        DeviceCSR.matrix_free = mf
+        try:
+            r = K0 @ t
+        finally:
+            DeviceCSR.matrix_free = True
+        assert float(r.abs().max()) <= 1e-12 * float(K0.diagonal_device().abs().max())
+    # checksum of checksums: sum of all assembled values == sum_e s_e * sum(Ke) (= 0 for a stiffness matrix) and
+    # trace == sum_e s_e trace(Ke)
+    Ke = pmb.AssembleStiffness(dom).elmat[0]
+    tr = float(K0.diagonal_device().sum())
+    assert abs(tr - float(xe.sum()) * np.trace(Ke)) <= 1e-10 * abs(tr)
+    # cantilever solve at full size: residual of the ASSEMBLED matrix <= 1e-8 although CG iterates matrix-free
+    ndof, bc, f = cantilever(Grid(nx, ny, nz))
+    asm = pmb.AssembleStiffness(dom, bc=bc)
+    s = 1e-9 + (1.0 - 1e-9) * flt(xe) ** 3
+    K = asm(s)
+    mgs = pmb.solvers.auto_multigrid(dom)
+    assert len(mgs) == 5
+    cg = pmb.solvers.CG(preconditioner=mgs[0], tol=1e-8)
+    fd = dv.to_device(f)
+    u = pmb.LinSolve(hermitian=True, solver=cg)(K, fd)
+    DeviceCSR.matrix_free = False
+    try:
+        relres = pmb.solvers.LinearSolver.residual(K, u, fd)
+    finally:
+        DeviceCSR.matrix_free = True
+    assert relres <= 1e-8
+    # symmetry of the constrained operator
+    p, q = dv.to_device(rng.standard_normal(n)), dv.to_device(rng.standard_normal(n))
+    lhs, rhs = float((K @ p) @ q), float(p @ (K @ q))
+    assert abs(lhs - rhs) <= 1e-9 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_host_numpy_module_chain_network(pmb):
+    """The drop-in use: numpy arrays at every module edge inside a Network (the way the reference's scripts run), with
+    the reference-style glue modules; response, sensitivity, reset and a second iteration with a changed design."""
+    nx, ny, nz = 16, 8, 8
+    P = ComplianceProblem(Grid(nx, ny, nz), kind="cantilever", tol=1e-8, min_size=4)
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    rng = np.random.default_rng(21)
+    x0 = rng.random(dom.nel)
+    sx = pmb.Signal("x", state=x0.copy())
+    with pmb.Network() as fn:
+        sy = pmb.DensityFilter(dom, radius=2.0)(sx)
+        ss = pmb.SIMP(1e-9, 3)(sy)
+        sK = pmb.AssembleStiffness(dom, bc=P.bc)(ss)
+        mgs = pmb.solvers.auto_multigrid(dom, min_size=4)
+        su = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=mgs[0], tol=1e-8))(sK, P.f)
+        sc = pmb.Compliance()(su, P.f)
+    for it in range(2):
+        c_ref = P.response(sx.state)
+        dx_ref = P.sensitivity()
+        assert isinstance(su.state, np.ndarray) and isinstance(sy.state, np.ndarray)
+        assert abs(float(sc.state) - c_ref) <= 1e-6 * abs(c_ref)
+        sc.sensitivity = 1.0
+        fn.sensitivity()
+        np.testing.assert_allclose(sx.sensitivity, dx_ref, rtol=1e-6, atol=1e-7 * np.abs(dx_ref).max())
+        fn.reset()
+        sx.state = np.clip(sx.state + 0.2 * (rng.random(dom.nel) - 0.5), 0, 1)
+        fn.response()
