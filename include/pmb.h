@@ -169,6 +169,11 @@ int pmb_stencil_corr(int inx, int iny, int inz, const double* in, int ox, int oy
 /* out = a / b */
 int pmb_vec_div(long long n, const double* a, const double* b, double* out, void* stream);
 
+/* OC update, one bisection candidate (pymoto/common/optimizers.py:425-435): xnew = clip(x sqrt(-min(dg,0)/lmid),
+ * max(xmin, x-move), min(xmax, x+move)), sum_out = sum(xnew) (deterministic). xnew may be NULL. ws: pmb_ws_doubles(). */
+int pmb_oc_candidate(long long n, const double* x, const double* dg, double move, double xmin, double xmax, double lmid,
+                     double* xnew, double* sum_out, double* ws, void* stream);
+
 /* SIMP glue kept on device for the resident path: s = xmin + (1-xmin) y^p ; dy = ds * p (1-xmin) y^(p-1) */
 int pmb_simp(long long n, double xmin, int p, const double* y, double* s, void* stream);
 int pmb_simp_bwd(long long n, double xmin, int p, const double* y, const double* ds, double* dy, void* stream);

@@ -19,9 +19,10 @@ from .filter import DensityFilter, Filter, FilterConv
 from .linalg import LinSolve
 from .glue import SIMP, Compliance
 from . import solvers
+from .optimizers import OC, minimize_oc
 from . import slab
 from ._lib import PmbError
 
 __all__ = ["Signal", "Module", "Network", "VoxelDomain", "DomainDefinition", "DeviceCSR", "DeviceDyad",
-           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "FilterConv", "LinSolve", "SIMP", "Compliance", "solvers", "slab",
+           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "FilterConv", "LinSolve", "SIMP", "Compliance", "solvers", "slab", "OC", "minimize_oc",
            "PmbError", "HAVE_PYMOTO"]

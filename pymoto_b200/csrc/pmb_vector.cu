@@ -281,3 +281,35 @@ extern "C" int pmb_simp_bwd(long long n, double xmin, int p, const double* y, co
   PMB_CHECK_LAUNCH("pmb_simp_bwd");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------- OC update
+// One bisection candidate of the optimality-criteria update (pymoto/common/optimizers.py:425-435):
+//   xnew_i = clip(x_i sqrt(-min(dg_i, 0) / lmid), max(xmin, x_i - move), min(xmax, x_i + move)),  sum_out = sum_i xnew_i
+// xnew may be NULL (only the volume is needed while bisecting).
+__global__ void __launch_bounds__(RED_THREADS) oc_candidate_kernel(long long n, const double* __restrict__ x, const double* __restrict__ dg,
+                                                                   double move, double xmin, double xmax, double lmid,
+                                                                   double* __restrict__ xnew, double* __restrict__ sum_out, double* ws) {
+  __shared__ double sm[4 * 8];
+  double v[1] = {0.0};
+  const long long stride = (long long)gridDim.x * RED_THREADS;
+  for (long long t = (long long)blockIdx.x * RED_THREADS + threadIdx.x; t < n; t += stride) {
+    const double xi = x[t];
+    const double g = fmin(dg[t], 0.0);
+    const double cand = xi * sqrt(-g / lmid);
+    const double lb = fmax(xmin, xi - move), ub = fmin(xmax, xi + move);
+    const double c = fmin(fmax(cand, lb), ub);
+    if (xnew) xnew[t] = c;
+    v[0] += c;
+  }
+  block_sum<1>(v, sm);
+  finish_reduction<1>(v, ws, sum_out);
+}
+
+extern "C" int pmb_oc_candidate(long long n, const double* x, const double* dg, double move, double xmin, double xmax, double lmid,
+                                double* xnew, double* sum_out, double* ws, void* stream) {
+  PMB_REQUIRE(x && dg && sum_out && ws, "pmb_oc_candidate: NULL pointer argument");
+  PMB_REQUIRE(lmid > 0.0, "pmb_oc_candidate: lmid must be positive");
+  oc_candidate_kernel<<<red_blocks_for(n), RED_THREADS, 0, (cudaStream_t)stream>>>(n, x, dg, move, xmin, xmax, lmid, xnew, sum_out, ws);
+  PMB_CHECK_LAUNCH("pmb_oc_candidate");
+  return 0;
+}

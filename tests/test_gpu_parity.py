@@ -173,7 +173,8 @@ def test_restriction_constants(pmb):
     assert np.all(r[1:-1, 1:-1, 1:-1] == 8.0) and r[0, 0, 0] == 3.375
     assert np.all(r[0, 1:-1, 1:-1] == 6.0) and np.all(r[0, 0, 1:-1] == 4.5)
     uf = dv.zeros(5 * 7 * 9)
-    _lib.call("pmb_prolong_add", gf, gc, dv.ptr(dv.to_device(np.ones(60))), dv.ptr(uf), dv.stream())
+    ones_c = dv.to_device(np.ones(60))
+    _lib.call("pmb_prolong_add", gf, gc, dv.ptr(ones_c), dv.ptr(uf), dv.stream())
     assert np.all(uf.cpu().numpy() == 1.0)
 
 
@@ -192,7 +193,8 @@ def test_dense_inverse_and_vector_kernels(pmb):
     np.testing.assert_allclose(Md.cpu().numpy().reshape(n, n), np.linalg.inv(M), rtol=0, atol=1e-12)
     x = rng.standard_normal(n)
     y = dv.empty(n)
-    _lib.call("pmb_dense_gemv", n, dv.ptr(Md), dv.ptr(dv.to_device(x)), dv.ptr(y), dv.stream())
+    xd = dv.to_device(x)
+    _lib.call("pmb_dense_gemv", n, dv.ptr(Md), dv.ptr(xd), dv.ptr(y), dv.stream())
     np.testing.assert_allclose(y.cpu().numpy(), np.linalg.solve(M, x), rtol=1e-10)
     # dots / lincomb, including empty and ragged lengths
     for m in [1, 31, 1000, 300001]:
@@ -628,3 +630,52 @@ def test_host_numpy_module_chain_network(pmb):
         fn.reset()
         sx.state = np.clip(sx.state + 0.2 * (rng.random(dom.nel) - 0.5), 0, 1)
         fn.response()
+
+
+def test_oc_update_and_minimize_oc_vs_reference(pmb):
+    """BASELINE.json configs[0] driven by the OC update on the device: 10 iterations of the 2-D MBB 100x50 problem against
+    the reference's own OC history (tests/golden/ref_oc_mbb100x50.npz: 369.3086 -> 101.4926, direct solver)."""
+    import torch
+    from pymoto_b200 import device as dv
+
+    g = load("oc_mbb100x50")
+    nx, ny = 100, 50
+    dom = pmb.VoxelDomain(nx, ny)
+    nodes = dom.nodes
+    bc = np.concatenate([2 * nodes[0, :].flatten(), 2 * nodes[nx, 0].flatten() + 1])
+    f = np.zeros(dom.nnodes * 2)
+    f[2 * nodes[0, ny].flatten() + 1] = -1.0
+    fd = dv.to_device(f)
+    sx = pmb.Signal("x", state=dv.to_device(np.full(dom.nel, 0.5)))
+    with pmb.Network() as fn:
+        sy = pmb.DensityFilter(dom, radius=2.0)(sx)
+        ss = pmb.SIMP(1e-9, 3)(sy)
+        sK = pmb.AssembleStiffness(dom, bc=bc)(ss)
+        mgs = pmb.solvers.auto_multigrid(dom)
+        su = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=mgs[0], tol=1e-10))(sK, fd)
+        sc = pmb.Compliance()(su, fd)
+    oc = pmb.OC(sx, sc, fn, verbosity=0)
+    hist = []
+    x = None
+    for it in range(10):
+        xnew, gval, dg = oc.step(x)
+        hist.append(gval)
+        x = xnew
+        assert float(xnew.min()) >= 0.0 and float(xnew.max()) <= 1.0
+        assert abs(float(xnew.mean()) - 0.5) < 1e-3  # volume kept by the bisection on the multiplier (l1l2tol = 1e-4)
+    np.testing.assert_allclose(hist, g["history"], rtol=1e-6)
+    np.testing.assert_allclose(x.cpu().numpy(), g["x10"], rtol=0, atol=1e-5)
+    # one candidate evaluation against numpy
+    xi, dgi = np.random.default_rng(0).random(1000), -np.random.default_rng(1).random(1000)
+    out, xn = dv.empty(1), dv.empty(1000)
+    from pymoto_b200 import _lib
+
+    xid, dgid = dv.to_device(xi), dv.to_device(dgi)  # keep the tensors alive across the raw-pointer call
+    _lib.call("pmb_oc_candidate", 1000, dv.ptr(xid), dv.ptr(dgid), 0.1, 0.0, 1.0, 0.37, dv.ptr(xn), dv.ptr(out),
+              dv.ptr(dv.workspace().red), dv.stream())
+    ref = np.clip(xi * np.sqrt(-dgi / 0.37), np.maximum(0.0, xi - 0.1), np.minimum(1.0, xi + 0.1))
+    np.testing.assert_allclose(xn.cpu().numpy(), ref, rtol=1e-15)
+    assert abs(float(out.item()) - ref.sum()) <= 1e-12 * ref.sum()
+    # minimize_oc runs to its stopping criterion on a small problem
+    oc2 = pmb.minimize_oc(sx, sc, function=fn, maxit=3, verbosity=0)
+    assert oc2.iter <= 3
