@@ -292,14 +292,15 @@ def run_b200(args, full):
     value = iters_per_sec * dof_scale
     compl = [float(c) for c in compl]
 
-    if args.profile and world == 1:
+    if args.profile:
         _lib.profile_times = {}
         chain.step(xs_dev[W + K])
         prof, _lib.profile_times = _lib.profile_times, None
         tot = sum(v[1] for v in prof.values())
-        print(f"# per-call breakdown of one step (synchronised calls), total {tot:.2f} ms", file=sys.stderr)
-        for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-            print(f"# {v[1]:9.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:5d}  avg {1e3 * v[1] / v[0]:9.1f} us  {k}", file=sys.stderr)
+        if rank == 0:
+            print(f"# per-call breakdown of one step (synchronised calls), total {tot:.2f} ms", file=sys.stderr)
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                print(f"# {v[1]:9.3f} ms {100 * v[1] / tot:5.1f}%  n={v[0]:5d}  avg {1e3 * v[1] / v[0]:9.1f} us  {k}", file=sys.stderr)
 
     # ---------------- end to end from pinned host buffers (x in, compliance + dc/dx out)
     e2e = None

@@ -54,13 +54,16 @@ __global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)
 
   const int tid = threadIdx.x;
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles blockIdx.x + i*gridDim.x
+  const long long amis = (long long)((reinterpret_cast<uintptr_t>(A) >> 3) & 1);
 
   // producer: issue the TMA bulk copy of this CTA's i-th tile into ring slot i % STAGES
   auto issue = [&](int i) {
     const int s = i % STAGES;
     const TileGeom t = tile_geom<NDOF, T>(g, (int)blockIdx.x + i * (int)gridDim.x, tiles_per_row);
-    const long long lo = t.e0 & ~1LL;
-    const long long hi = (t.e1 + 1) & ~1LL;
+    // 16-byte aligned window [lo, hi) around the tile's entries; `amis` = 1 when A itself sits on an odd double
+    // (a sub-slab view of a larger matrix), in which case the window may start one double before A
+    const long long lo = ((t.e0 + amis) & ~1LL) - amis;
+    const long long hi = ((t.e1 + amis + 1) & ~1LL) - amis;
     const unsigned bytes = (unsigned)((hi - lo) * sizeof(double));
     mbar_expect_tx(&full_bar[s], bytes);
     tma_load_1d(sTiles + (size_t)s * TD, A + lo, bytes, &full_bar[s], stream_hint != 0);
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)
     {
       const int L = cx * t.cy * t.cz * NDOF;
       const long long per = (long long)(NDOF * NDOF) * t.cy * t.cz;
-      const double* rowp = sTiles + (size_t)s * TD + ((t.e0 - (t.e0 & ~1LL)) + per * (pre1(i, g.NX) - pre1(t.i0, g.NX)));
+      const double* rowp = sTiles + (size_t)s * TD + ((t.e0 - (((t.e0 + amis) & ~1LL) - amis)) + per * (pre1(i, g.NX) - pre1(t.i0, g.NX)));
 #pragma unroll
       for (int l = 0; l < LINES; ++l) {
         if (!lvalid[l]) continue;
@@ -277,7 +280,7 @@ extern "C" int pmb_spmv(const pmb_grid* p, int mode, const double* data, const d
   PMB_REQUIRE(mode == MODE_SPMV || b, "pmb_spmv: b required for residual / Jacobi");
   PMB_REQUIRE(mode != MODE_JACOBI || diag, "pmb_spmv: diag required for Jacobi");
   PMB_REQUIRE(!dot_out || ws, "pmb_spmv: workspace required for the fused dot products");
-  PMB_REQUIRE((reinterpret_cast<size_t>(data) & 15) == 0, "pmb_spmv: data must be 16-byte aligned");
+  PMB_REQUIRE((reinterpret_cast<size_t>(data) & 7) == 0, "pmb_spmv: data must be 8-byte aligned");
   Geo g = make_geo(p);
   cudaStream_t st = (cudaStream_t)stream;
   switch (g.ndof) {

@@ -9,6 +9,8 @@ With a slab decomposition (pymoto_b200/slab.py) the object holds the rows of thi
 multiplies are views into buffers padded by one halo plane on each side (:meth:`new_vec`), refreshed from the
 neighbours by :meth:`exchange` before every operator application.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -21,6 +23,11 @@ def make_grid(nx, ny, nz, ndof, kz0=0, nzl=None):
 
 
 class DeviceCSR:
+    # Distributed operator applications without fused dot products are split into interior planes (launched while the
+    # halo planes are in flight) and the two boundary planes (launched once they arrived).
+    overlap_halo = os.environ.get("PMB_OVERLAP_HALO", "1") != "0"
+    overlap_min_rows = 3_000_000  # below this the three sub-launches cost more host time than the exchange they hide
+
     # Apply finest-level operators matrix-free (from the element scaling vector, pmb_elem.cu) when the assembly module
     # attached its generator; the assembled values stay the source of truth for everything else.  Set to False to
     # stream the CSR values on every level.
@@ -46,6 +53,7 @@ class DeviceCSR:
         self.bc_mask = bc_mask  # uint8 per dof or None (set by the assembly module; informational)
         self._indptr = self._indices = None
         self._diag = self._nnz_off = None
+        self._entry_offsets = {}
         self.generator = None  # dict(ke=host ndarray, s=device tensor, mask=device uint8 or None, bcdiag=float)
 
     # ---- values
@@ -112,23 +120,58 @@ class DeviceCSR:
         return self.diagonal_device().cpu().numpy()
 
     # ---- products
+    def _launch(self, gen, grid, mode, data_ptr, s_ptr, mask_ptr, x_ptr, b_ptr, diag_ptr, w, y_ptr, dotv_ptr, dot_ptr, ws_ptr):
+        if gen is None:
+            _lib.call("pmb_spmv", grid, mode, data_ptr, x_ptr, b_ptr, diag_ptr, float(w), y_ptr, dotv_ptr, dot_ptr, ws_ptr,
+                      dv.stream())
+        else:
+            _lib.call("pmb_elem_spmv", grid, mode, gen["ke"].ctypes.data, s_ptr, mask_ptr, float(gen["bcdiag"]), x_ptr, b_ptr,
+                      diag_ptr, float(w), y_ptr, dotv_ptr, dot_ptr, ws_ptr, dv.stream())
+
     def apply(self, mode, x, y, b=None, diag=None, w=0.0, dotv=None, dot_out=None):
         """Raw kernel call on device tensors: y = A x | b - A x | x + w (b - A x)/diag, optional fused dots."""
         gen = self.generator if DeviceCSR.matrix_free else None
+        g = self.grid
         ws = None
         if dot_out is not None:
-            ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles" if gen is None else "pmb_elem_ws_doubles", self.grid))
-        if self.comm is not None:
-            self.exchange(x)
-        if gen is None:
-            _lib.call("pmb_spmv", self.grid, mode, dv.ptr(self._buf), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y),
-                      dv.ptr(dotv), dv.ptr(dot_out), dv.ptr(ws), dv.stream())
-        else:
-            _lib.call("pmb_elem_spmv", self.grid, mode, gen["ke"].ctypes.data, dv.ptr(gen["s"]), dv.ptr(gen["mask"]),
-                      float(gen["bcdiag"]), dv.ptr(x), dv.ptr(b), dv.ptr(diag), float(w), dv.ptr(y), dv.ptr(dotv),
-                      dv.ptr(dot_out), dv.ptr(ws), dv.stream())
-        if dot_out is not None and self.comm is not None:
-            self.comm.allreduce_(dot_out)
+            ws = dv.workspace().spmv_ws(_lib.query("pmb_spmv_ws_doubles" if gen is None else "pmb_elem_ws_doubles", g))
+
+        def P(t):
+            return None if t is None else t.data_ptr()
+
+        s_ptr = P(gen["s"]) if gen is not None else None
+        mask_ptr = P(gen["mask"]) if gen is not None else None
+        if self.comm is None or dot_out is not None or not DeviceCSR.overlap_halo or g.nzl < 3 or self.n < DeviceCSR.overlap_min_rows:
+            if self.comm is not None:
+                self.exchange(x)
+            self._launch(gen, g, mode, P(self._buf), s_ptr, mask_ptr, P(x), P(b), P(diag), w, P(y), P(dotv), P(dot_out), P(ws))
+            if dot_out is not None and self.comm is not None:
+                self.comm.allreduce_(dot_out)
+            return y
+        # ---- distributed, overlapped: post the halo exchange, compute the interior planes, then the two boundary planes
+        base = x._base if x._base is not None else x
+        off = x.storage_offset()
+        if x._base is None or off < self.plane or base.numel() < off + self.n + self.plane:
+            raise _lib.PmbError("distributed operator input must come from DeviceCSR.new_vec() (halo-padded storage)")
+        reqs = self.comm.exchange_start(base, off, self.n, self.plane)
+        lay = g.nx * g.ny  # elements per layer (matrix-free generator)
+
+        def sub(k_rel, nplanes):
+            """Launch on owned planes [k_rel, k_rel + nplanes) (relative to kz0): every pointer moves with the sub-slab."""
+            sg = make_grid(g.nx, g.ny, g.nz, g.ndof, g.kz0 + k_rel, nplanes)
+            dofs = k_rel * self.plane
+            first_entry = self._entry_offsets.get(k_rel)
+            if first_entry is None:
+                first_entry = 0 if k_rel == 0 else _lib.query("pmb_nnz", make_grid(g.nx, g.ny, g.nz, g.ndof, g.kz0, k_rel))
+                self._entry_offsets[k_rel] = first_entry
+            sh = lambda p, n, sz: None if p is None else p + n * sz  # noqa: E731
+            self._launch(gen, sg, mode, sh(P(self._buf), first_entry, 8), sh(s_ptr, k_rel * lay, 8), sh(mask_ptr, dofs, 1),
+                         sh(P(x), dofs, 8), sh(P(b), dofs, 8), sh(P(diag), dofs, 8), w, sh(P(y), dofs, 8), None, None, None)
+
+        sub(1, g.nzl - 2)
+        self.comm.exchange_finish(reqs)
+        sub(0, 1)
+        sub(g.nzl - 1, 1)
         return y
 
     def matvec_device(self, x, out=None):

@@ -125,6 +125,28 @@ class SlabComm:
                 req.wait()
         self.exchanges += 1
 
+    def exchange_start(self, base, own_offset, own_len, plane):
+        """Post the halo exchange (both sides, one plane) without waiting: returns the request handles.  The transfers
+        run on the communicator's own stream, ordered after everything already queued on the current stream."""
+        if not self.active:
+            return []
+        p = self.part
+        ops = []
+        if p.lower is not None:
+            ops.append(dist.P2POp(dist.isend, base[own_offset:own_offset + plane], p.lower, self.group))
+            ops.append(dist.P2POp(dist.irecv, base[own_offset - plane:own_offset], p.lower, self.group))
+        if p.upper is not None:
+            ops.append(dist.P2POp(dist.isend, base[own_offset + own_len - plane:own_offset + own_len], p.upper, self.group))
+            ops.append(dist.P2POp(dist.irecv, base[own_offset + own_len:own_offset + own_len + plane], p.upper, self.group))
+        self.exchanges += 1
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def exchange_finish(reqs):
+        """Make the current stream wait for a posted exchange."""
+        for r in reqs:
+            r.wait()
+
     def allreduce_(self, t):
         if self.active:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -168,7 +190,7 @@ class SlabContext:
 _context = None
 
 
-def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=1_000_000):
+def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=4_000_000):
     """Decompose ``domain`` in z over the ranks of the (default) process group. Call after init_process_group.
 
     ``n_levels`` = number of matrices in the multigrid hierarchy (GeometricMultigrid operators + 1).  Levels with

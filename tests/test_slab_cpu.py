@@ -30,6 +30,7 @@ def test_partition_arithmetic():
     # dof threshold keeps small levels replicated
     dofs = [3 * ((512 >> l) + 1) * ((256 >> l) + 1) * ((256 >> l) + 1) for l in range(7)]
     assert SlabPartition(256, 8, 0, n_levels=7, level_dofs=dofs, min_dofs=1_000_000).n_dist == 3
+    assert SlabPartition(256, 8, 0, n_levels=7, level_dofs=dofs, min_dofs=4_000_000).n_dist == 2
     # the coarsest level is never split; single rank owns everything
     assert SlabPartition(16, 2, 0, n_levels=2).n_dist == 1
     s = SlabPartition(32, 1, 0, n_levels=3)
