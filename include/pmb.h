@@ -169,6 +169,10 @@ int pmb_stencil_corr(int inx, int iny, int inz, const double* in, int ox, int oy
 /* out = a / b */
 int pmb_vec_div(long long n, const double* a, const double* b, double* out, void* stream);
 
+/* Multi-GPU halo mailboxes: two independent n-double copies in one launch (dst may be PEER memory mapped through
+ * symmetric memory: the stores then travel over NVLink).  Any (src, dst) pair with a NULL member is skipped. */
+int pmb_halo_copy2(long long n, const double* src0, double* dst0, const double* src1, double* dst1, void* stream);
+
 /* OC update, one bisection candidate (pymoto/common/optimizers.py:425-435): xnew = clip(x sqrt(-min(dg,0)/lmid),
  * max(xmin, x-move), min(xmax, x+move)), sum_out = sum(xnew) (deterministic). xnew may be NULL. ws: pmb_ws_doubles(). */
 int pmb_oc_candidate(long long n, const double* x, const double* dg, double move, double xmin, double xmax, double lmid,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "pmb_pad_scatter": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pmb_stencil_corr": (_I, [_I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
+    "pmb_halo_copy2": (_I, [_LL, _P, _P, _P, _P, _P]),
     "pmb_oc_candidate": (_I, [_LL, _P, _P, _D, _D, _D, _D, _P, _P, _P, _P]),
     "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
     "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_consta
       const int row = 2 * q + half;
       const int ty = row % TY, tz = row / TY;
       const int j = j0 - 1 + ty, k = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
-      inb[q] = colin && row < TZ * TY && j >= 0 && j < g.NY && k >= 0 && k < g.NZ;
+      // planes beyond the slab's upper halo (k > kz0 + nzl) are never needed and may not be mapped
+      inb[q] = colin && row < TZ * TY && j >= 0 && j < g.NY && k >= 0 && k < g.NZ && k <= g.kz0 + g.nzl;
       const long long idx = inb[q] ? (((long long)(k - g.kz0) * g.NY + j) * g.NX + (i0 - 1)) * NDOF + col : safe;
       xv[q] = __ldg(x + idx);
       mk[q] = mask ? __ldg(mask + idx) : (unsigned char)0;
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_consta
       const int p = tid + 256 * q;
       const int tx = p % (BX + 1), ty = (p / (BX + 1)) % (BY + 1), tz = p / ((BX + 1) * (BY + 1));
       const int ei = i0 - 1 + tx, ej = j0 - 1 + ty, ek = DIM3 ? (g.kz0 + kl0 - 1 + tz) : 0;
-      sin[q] = p < NS && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE;
+      // element layers above the last owned node plane belong to the next rank and are not needed
+      sin[q] = p < NS && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE && (!DIM3 || ek < g.kz0 + g.nzl);
       // safe address: an element of the brick's own first node (exists unless the brick starts on the far faces)
       const long long sidx = sin[q] ? ((long long)(ek - (DIM3 ? g.kz0 : 0)) * g.ny + ej) * g.nx + ei : 0;
       sv[q] = __ldg(s + sidx);

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(FTX* FTY* FTZ) filter_kernel(int nx, int ny, i
     int sx = q % SX, sy = (q / SX) % SY, sz = q / (SX * SY);
     int gx = bx + sx - d, gy = by + sy - d, gz = ez0 + bz + sz - dz;  // global element indices
     double v = 0.0;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nzE)
+    // (layers further than dz from the produced range are never used and, on a slab, may not be mapped)
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny && gz >= 0 && gz < nzE && gz >= ez0 - dz && gz < ez0 + nezl + dz)
       v = in ? __ldg(in + ((long long)(gz - ez0) * ny + gy) * nx + gx) : 1.0;
     tile[q] = v;
   }

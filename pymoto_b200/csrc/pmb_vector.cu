@@ -313,3 +313,31 @@ extern "C" int pmb_oc_candidate(long long n, const double* x, const double* dg, 
   PMB_CHECK_LAUNCH("pmb_oc_candidate");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------- halo mailboxes (multi-GPU)
+// Neighbour halo exchange over NVLink peer memory: every rank owns a mailbox in symmetric memory; pmb_halo_pack stores
+// this rank's boundary planes straight into the mailboxes of its z-neighbours (peer pointers, plain st.global over
+// NVLink), a device-side barrier follows (torch symmetric-memory signal pads), then pmb_halo_unpack moves the received
+// planes into the halo planes of the destination vector.  Either destination / source may be NULL (domain ends or a
+// one-sided exchange).
+__global__ void __launch_bounds__(256) halo_copy2_kernel(long long n, const double* __restrict__ src0, double* __restrict__ dst0,
+                                                          const double* __restrict__ src1, double* __restrict__ dst1) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += stride) {
+    if (t < n) {
+      if (src0 && dst0) dst0[t] = src0[t];
+    } else {
+      if (src1 && dst1) dst1[t - n] = src1[t - n];
+    }
+  }
+}
+
+extern "C" int pmb_halo_copy2(long long n, const double* src0, double* dst0, const double* src1, double* dst1, void* stream) {
+  PMB_REQUIRE(n > 0, "pmb_halo_copy2: invalid length");
+  if (!(src0 && dst0) && !(src1 && dst1)) return 0;
+  long long blocks = (2 * n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  halo_copy2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, src0, dst0, src1, dst1);
+  PMB_CHECK_LAUNCH("pmb_halo_copy2");
+  return 0;
+}

@@ -141,7 +141,8 @@ class DeviceCSR:
 
         s_ptr = P(gen["s"]) if gen is not None else None
         mask_ptr = P(gen["mask"]) if gen is not None else None
-        if self.comm is None or dot_out is not None or not DeviceCSR.overlap_halo or g.nzl < 3 or self.n < DeviceCSR.overlap_min_rows:
+        if (self.comm is None or dot_out is not None or not DeviceCSR.overlap_halo or g.nzl < 3 or self.n < DeviceCSR.overlap_min_rows
+                or self.comm.fast):  # mailbox exchanges are cheap enough to stay on the compute stream
             if self.comm is not None:
                 self.exchange(x)
             self._launch(gen, g, mode, P(self._buf), s_ptr, mask_ptr, P(x), P(b), P(diag), w, P(y), P(dotv), P(dot_out), P(ws))

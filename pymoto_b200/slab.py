@@ -9,6 +9,8 @@ tensors, which is how the host-side logic is tested without a GPU).  The data pa
 steps: (1) neighbour halo planes before an operator application / transfer / filter, (2) a sum all-reduce of the
 CG / LDAS dot products, (3) one gather of the first replicated multigrid level per V-cycle.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -93,6 +95,55 @@ class SlabComm:
         self.group = group
         self.exchanges = 0
         self.allreduces = 0
+        self.fast = False  # symmetric-memory mailboxes enabled (CUDA + NCCL only)
+        self.fast_exchanges = 0
+
+    def enable_mailboxes(self, max_doubles, device):
+        """Halo exchange through symmetric memory instead of NCCL send/recv: every rank gets a mailbox of
+        2 slots x 2 directions x ``max_doubles``; neighbours store their boundary planes into it with a copy kernel
+        (peer stores over NVLink), a device-side barrier orders the stores before the unpack.  Two slots alternate so
+        that one barrier per exchange is enough (a slot is rewritten two exchanges later, i.e. after another barrier
+        that the receiver only reaches once it has unpacked)."""
+        if not self.active:
+            return False
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._cap = int(max_doubles)
+        self._mb = symm_mem.empty(4 * self._cap, dtype=torch.float64, device=device)
+        self._mb.zero_()
+        self._hdl = symm_mem.rendezvous(self._mb, dist.group.WORLD if self.group is None else self.group)
+        p = self.part
+        self._peer_lo = self._hdl.get_buffer(p.lower, (4 * self._cap,), torch.float64) if p.lower is not None else None
+        self._peer_hi = self._hdl.get_buffer(p.upper, (4 * self._cap,), torch.float64) if p.upper is not None else None
+        self._slot = 0
+        self.fast = True
+        return True
+
+    def _fast_exchange(self, base, own_offset, own_len, n, lower, upper):
+        from . import _lib
+
+        p = self.part
+        st = torch.cuda.current_stream().cuda_stream
+        o = (self._slot & 1) * 2 * self._cap
+        self._slot += 1
+        b0 = base.data_ptr() + 8 * own_offset  # first owned entry
+        # box layout per slot: [0, cap) = planes coming from the rank below, [cap, 2 cap) = from the rank above
+        # `upper` = I want my upper halo filled = every rank sends its bottom planes down; `lower` = top planes go up
+        src0 = dst0 = src1 = dst1 = None
+        if upper and self._peer_lo is not None:
+            src0, dst0 = b0, self._peer_lo.data_ptr() + 8 * (o + self._cap)
+        if lower and self._peer_hi is not None:
+            src1, dst1 = b0 + 8 * (own_len - n), self._peer_hi.data_ptr() + 8 * o
+        _lib.call("pmb_halo_copy2", n, src0, dst0, src1, dst1, st)
+        self._hdl.barrier(channel=0)
+        src0 = dst0 = src1 = dst1 = None
+        if lower and p.lower is not None:
+            src0, dst0 = self._mb.data_ptr() + 8 * o, b0 - 8 * n
+        if upper and p.upper is not None:
+            src1, dst1 = self._mb.data_ptr() + 8 * (o + self._cap), b0 + 8 * own_len
+        _lib.call("pmb_halo_copy2", n, src0, dst0, src1, dst1, st)
+        self.exchanges += 1
+        self.fast_exchanges += 1
 
     @property
     def active(self):
@@ -109,6 +160,8 @@ class SlabComm:
             return
         p = self.part
         n = plane * width
+        if self.fast and base.is_cuda and base.dtype == torch.float64 and n <= self._cap:
+            return self._fast_exchange(base, own_offset, own_len, n, lower, upper)
         ops = []
         if upper:  # data flows downwards: I send my bottom planes to the lower neighbour, receive from the upper
             if p.lower is not None:
@@ -190,7 +243,7 @@ class SlabContext:
 _context = None
 
 
-def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=4_000_000):
+def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=1_000_000, mailboxes=True):
     """Decompose ``domain`` in z over the ranks of the (default) process group. Call after init_process_group.
 
     ``n_levels`` = number of matrices in the multigrid hierarchy (GeometricMultigrid operators + 1).  Levels with
@@ -202,7 +255,16 @@ def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3
     level_dofs = [ndof * ((nx >> l) + 1) * ((ny >> l) + 1) * ((nz >> l) + 1) for l in range(max(n_levels, 1))]
     part = SlabPartition(nz, world, rank, n_levels=n_levels, min_planes=min_planes, force_n_dist=force_n_dist,
                          level_dofs=level_dofs, min_dofs=min_dofs)
-    _context = SlabContext(part, SlabComm(part, group))
+    comm = SlabComm(part, group)
+    _context = SlabContext(part, comm)
+    if (mailboxes and world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+            and os.environ.get("PMB_HALO_MAILBOX", "1") != "0"):
+        try:  # nodal-vector planes of every level fit the finest level's plane
+            comm.enable_mailboxes((nx + 1) * (ny + 1) * ndof, torch.device("cuda", torch.cuda.current_device()))
+        except Exception as e:  # symmetric memory unavailable (no P2P access, old driver): NCCL send/recv stays in use
+            import warnings
+
+            warnings.warn(f"symmetric-memory halo mailboxes unavailable ({e}); using NCCL send/recv")
     return _context
 
 
