@@ -158,3 +158,40 @@ def test_module_runtime_protocol():
     assert sx.sensitivity.tolist() == [4.0, 4.0, 4.0]
     fn.reset()
     assert sx.sensitivity is None and sy.sensitivity is None
+
+
+def test_header_and_binding_agree_on_arity():
+    """Every prototype in include/pmb.h has the same number of parameters as its ctypes signature in _lib.SIGNATURES."""
+    from pymoto_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "pmb.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(pmb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 30
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert name in _lib.SIGNATURES, name
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_filterconv_axis_maps_match_reference_padding():
+    """The per-axis index maps of FilterConv reproduce the reference's np.pad sequence (filter.py:99-160), including
+    mixed boundary types; checked against the live reference where it is available."""
+    from pymoto_b200.filter import FilterConv
+    from _refimport import import_reference
+
+    m, c = FilterConv._axis_map(6, 2, "symmetric", "symmetric")
+    assert m.tolist() == [1, 0, 0, 1, 2, 3, 4, 5, 5, 4]
+    m, c = FilterConv._axis_map(6, 2, 0.5, "wrap")
+    assert m.tolist() == [-1, -1, 0, 1, 2, 3, 4, 5, 0, 1] and c[:2].tolist() == [0.5, 0.5]
+    assert FilterConv._axis_map(5, 0, "edge", "edge")[0].tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        FilterConv._axis_map(5, 1, "mirror", "edge")
+    pym = import_reference()
+    if pym is None:
+        return
+    d = pym.VoxelDomain(7, 1, 1)
+    for bc0, bc1 in [("symmetric", "edge"), ("edge", "wrap"), ("wrap", "symmetric"), ("wrap", "wrap"), ("edge", "edge")]:
+        ref = pym.FilterConv(d, weights=np.ones((5, 1, 1)), xmin_bc=bc0, xmax_bc=bc1)
+        assert ref.el3d_pad[:, 0, 0].tolist() == FilterConv._axis_map(7, 2, bc0, bc1)[0].tolist(), (bc0, bc1)
