@@ -93,8 +93,14 @@ def cpu_arm(size, steps, warmup):
 def pick_cpu_size(full, steps, warmup, explicit):
     if explicit is not None:
         return tuple(explicit)
-    # ~1.4 s / iteration at 64x32x32 and ~12 s at 128x64x64; keep the whole arm within a few minutes
-    if (steps + warmup) * 12 + 60 <= 200 and min(full) >= 64:
+    # ~2 s / iteration at 64x32x32 and ~9-12 s at 128x64x64 (10 GB resident); keep the whole arm within a few minutes
+    try:
+        import psutil
+
+        enough_ram = psutil.virtual_memory().available > 24e9
+    except Exception:
+        enough_ram = False
+    if (steps + warmup) * 12 + 60 <= 200 and min(full) >= 64 and enough_ram:
         return (128, 64, 64)
     return (64, 32, 32) if min(full) >= 32 else tuple(full)
 
