@@ -388,6 +388,25 @@ def run_b200(args, full):
                 "fine_level_operator_launches_per_step": (fine_csr + fine_mf) / K,
                 "stencil_csr_launches_per_step": csr_calls / K,
                 "share_of_step": (fine_csr / K) * kern_ms / step_avg_ms if not was_mf else None}
+    # the same kernel on the largest operator it streams inside the default (matrix-free level 0) iteration: level 1
+    if len(chain.mgs) > 1 and chain.mgs[0].Ac is not None and chain.mgs[1]._buf is not None:
+        A1, mg1 = chain.mgs[0].Ac, chain.mgs[1]
+        a1, a2, b1, D1 = mg1._buf["u"], mg1._buf["u2"], mg1._buf["t"], mg1.smoother.D
+        for _ in range(3):
+            A1.apply(_lib.JACOBI, a1, a2, b=b1, diag=D1, w=0.5)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(20):
+            A1.apply(_lib.JACOBI, a1, a2, b=b1, diag=D1, w=0.5)
+            a1, a2 = a2, a1
+        q1.record()
+        torch.cuda.synchronize()
+        l1_ms = q0.elapsed_time(q1) / 20
+        l1_bytes = 8 * A1.nnz + 32 * A1.shape[0]
+        roofline["level1"] = {"kernel_ms": l1_ms, "algorithmic_bytes": l1_bytes, "achieved": l1_bytes / (l1_ms * 1e-3) / 1e9,
+                              "frac": l1_bytes / (l1_ms * 1e-3) / 1e9 / peak,
+                              "launches_per_step": sum(v for (nm, det), v in stats.items() if nm == "pmb_spmv" and det[0] == full[0] // 2) / K}
     matrix_free = None
     if was_mf:
         mf_ms = time_sweeps()
@@ -398,6 +417,26 @@ def run_b200(args, full):
                        "speedup_vs_streaming_assembled_values": kern_ms / mf_ms,
                        "assembled_layout_time_at_100pct_hbm_peak_ms": alg_bytes / (peak * 1e9) * 1e3,
                        "step_ms_if_level0_streamed_at_100pct_hbm_peak": step_avg_ms + (fine_mf / K) * (alg_bytes / (peak * 1e9) * 1e3 - mf_ms)}
+
+    # ---------------- the same K steps with every level streamed from its assembled CSR values (north-star layout)
+    csr_streamed = None
+    if was_mf and world == 1 and not args.no_e2e:
+        DeviceCSR.matrix_free = False
+        chain.ls._u_dev = None
+        for i in range(W):
+            chain.step(xs_dev[i])
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(K):
+            chain.step(xs_dev[W + i])
+        c1.record()
+        torch.cuda.synchronize()
+        DeviceCSR.matrix_free = True
+        cms = c0.elapsed_time(c1) / K
+        csr_streamed = {"value": 1e3 / cms, "unit": UNIT, "ms_per_step": cms,
+                        "fine_kernel_share_of_step": (fine_mf / K) * kern_ms / cms,
+                        "note": "same workload with DeviceCSR.matrix_free = False (bench.py --csr)"}
 
     # ---------------- CPU baseline (bounded sample), rank 0 only
     cpu = None
@@ -426,7 +465,7 @@ def run_b200(args, full):
                        "exchange + dot-product all-reduce; value = iterations/s x dof / 12.83M (weak scaling)",
                        "iters_per_sec_this_grid": iters_per_sec},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "matrix_free": matrix_free,
-            "cpu_baseline": cpu,
+            "csr_streamed": csr_streamed, "cpu_baseline": cpu,
             "cg_iterations": cg_its, "ms_per_step_list": step_ms, "compliance": compl,
         }
         sys.stdout.flush()
