@@ -64,13 +64,13 @@ __global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __re
   for (int q = threadIdx.x; q < ke_ld * ke_ld; q += blockDim.x) sKe[q] = Ke[q];
   __syncthreads();
 
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long nslots = g.nOwned * 27;
-  if (t >= nslots) return;
-  int s = (int)(t % 27);
-  long long ln = t / 27;
-  int i, j, k;
-  node_ijk(g, ln, i, j, k);
+  // 3-D launch: blockIdx.y = j, blockIdx.z = owned plane, blockIdx.x * 256 + threadIdx.x = i * 27 + slot.  All index
+  // arithmetic below is 32-bit without runtime divisions (the kernel is instruction-bound, not bandwidth-bound, otherwise)
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= g.NX * 27) return;
+  const int i = q / 27, s = q - i * 27;
+  const int j = blockIdx.y, k = g.kz0 + blockIdx.z;
+  const long long ln = ((long long)blockIdx.z * g.NY + j) * g.NX + i;
   int dk = s / 9 - 1, dj = (s / 3) % 3 - 1, di = s % 3 - 1;
   int ci = i + di, cj = j + dj, ck = k + dk;
   if (ci < 0 || ci >= g.NX || cj < 0 || cj >= g.NY || ck < 0 || ck >= g.NZ) return;
@@ -135,8 +135,8 @@ extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke, const double* x
   if (validate_grid(p, "pmb_assemble")) return 1;
   PMB_REQUIRE(Ke && x && data, "pmb_assemble: NULL pointer argument");
   Geo g = make_geo(p);
-  long long nslots = g.nOwned * 27;
-  unsigned blocks = (unsigned)((nslots + 255) / 256);
+  PMB_REQUIRE(g.NY <= 65535 && g.nzl <= 65535, "pmb_assemble: grid too large for the 3-D launch");
+  dim3 blocks((g.NX * 27 + 255) / 256, g.NY, g.nzl);
   cudaStream_t st = (cudaStream_t)stream;
   switch (g.ndof) {
     case 1: assemble_kernel<1><<<blocks, 256, 0, st>>>(g, Ke, x, bcmask, bcdiagval, data); break;

@@ -186,8 +186,8 @@ class GeometricMultigrid(Preconditioner):
         gcl = self._gc_local
         # two streaming passes; between them the lower halo plane of the column-collapsed intermediate is fetched
         # from the rank below (its top owned fine plane contributes to my first coarse plane)
-        bplane = (g.nx + 1) * (g.ny + 1) * 27 * g.ndof * g.ndof
         nwork = _lib.query("pmb_galerkin_ws_doubles", g)
+        bplane = nwork // g.nzl  # one node plane of the intermediate
         work = dv.workspace().galerkin_ws(nwork + bplane)
         st = dv.stream()
         _lib.call("pmb_galerkin_cols", g, gcl, dv.ptr(A._buf), work.data_ptr() + 8 * bplane, st)
