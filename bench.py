@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="sample grid of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--problem", default="cantilever", choices=["cantilever", "thermal"],
+                    help="cantilever = BASELINE configs[2]/[3] (metric); thermal = configs[4] (scalar conduction heat sink)")
     ap.add_argument("--csr", action="store_true", help="stream the assembled CSR values on every level (no matrix-free level 0)")
     ap.add_argument("--kernel-only", action="store_true", help="only the dominant-kernel loop (for ncu captures)")
     ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event breakdown of one step (diagnostic)")
@@ -173,32 +175,39 @@ class GpuChain:
     """The design iteration through the public Module API of pymoto_b200 (device-resident tensors).  With more than one
     rank the grid is split into z-slabs (pymoto_b200/slab.py) and every rank holds its own element layers / node planes."""
 
-    def __init__(self, size, world=1):
+    def __init__(self, size, world=1, problem="cantilever"):
         import pymoto_b200 as pmb
         from pymoto_b200 import device as dv
 
         self.pmb, self.dv = pmb, dv
         nx, ny, nz = size
         self.dom = dom = pmb.VoxelDomain(nx, ny, nz)
-        ndof = 3
+        ndof = 3 if problem == "cantilever" else 1
         self.mgs = pmb.solvers.auto_multigrid(dom)
-        self.ctx = pmb.slab.init(dom, n_levels=len(self.mgs) + 1) if world > 1 else pmb.slab.context(nz)
+        self.ctx = pmb.slab.init(dom, n_levels=len(self.mgs) + 1, ndof=ndof) if world > 1 else pmb.slab.context(nz)
         k0, k1 = self.ctx.part.planes(0) if world > 1 else (0, nz + 1)
         self.e0, self.e1 = self.ctx.part.elem_layers(0) if world > 1 else (0, nz)
         self.lay = nx * ny
         plane = (nx + 1) * (ny + 1) * ndof
-        nodes_face = (np.arange(nz + 1)[:, None] * (ny + 1) + np.arange(ny + 1)[None, :]).ravel() * (nx + 1)  # i = 0
-        bc = (nodes_face[:, None] * ndof + np.arange(ndof)[None, :]).ravel()  # global dof numbers
-        f = np.zeros((k1 - k0) * plane)  # this rank's node planes
-        kl = nz // 2
-        if k0 <= kl < k1:
-            load_nodes = ((kl - k0) * (ny + 1) + np.arange(ny + 1)) * (nx + 1) + nx  # i = nx, k = nz/2
-            f[load_nodes * ndof + 2] = 1.0
+        if problem == "cantilever":
+            nodes_face = (np.arange(nz + 1)[:, None] * (ny + 1) + np.arange(ny + 1)[None, :]).ravel() * (nx + 1)  # i = 0
+            bc = (nodes_face[:, None] * ndof + np.arange(ndof)[None, :]).ravel()  # global dof numbers
+            f = np.zeros((k1 - k0) * plane)  # this rank's node planes
+            kl = nz // 2
+            if k0 <= kl < k1:
+                load_nodes = ((kl - k0) * (ny + 1) + np.arange(ny + 1)) * (nx + 1) + nx  # i = nx, k = nz/2
+                f[load_nodes * ndof + 2] = 1.0
+        else:  # heat sink: T = 0 on a centred patch of face i = 0, unit heat load on every node with i >= 1
+            kk, jj = np.meshgrid(np.arange(nz // 4, (nz + 1) - nz // 4), np.arange(ny // 4, (ny + 1) - ny // 4), indexing="ij")
+            bc = ((kk * (ny + 1) + jj) * (nx + 1)).ravel()
+            f = np.ones(((k1 - k0), ny + 1, nx + 1))
+            f[:, :, 0] = 0.0
+            f = f.ravel()
         self.ndof_global = dom.nnodes * ndof
         self.f = dv.to_device(f)
         self.flt = pmb.DensityFilter(dom, radius=RADIUS)
         self.simp = pmb.SIMP(XMIN, 3)
-        self.asm = pmb.AssembleStiffness(dom, bc=np.sort(bc))
+        self.asm = (pmb.AssembleStiffness if problem == "cantilever" else pmb.AssemblePoisson)(dom, bc=np.sort(bc))
         self.cg = pmb.solvers.CG(preconditioner=self.mgs[0], tol=TOL)
         self.ls = pmb.LinSolve(hermitian=True, solver=self.cg)
         self.compl = pmb.Compliance()
@@ -243,7 +252,7 @@ def run_b200(args, full):
         from pymoto_b200.matrix import DeviceCSR as _D
 
         _D.matrix_free = False
-    chain = GpuChain(full, world)
+    chain = GpuChain(full, world, args.problem)
     W, K = args.warmup, args.steps
     xs_host = design_sequence(chain.dom.nel, W + K + (1 if args.profile else 0), keep=chain.local)
     nel = xs_host[0].size  # elements held by this rank
@@ -294,7 +303,7 @@ def run_b200(args, full):
     # one slab-decomposed job over all ranks.  Weak scaling: the grid grows with the rank count, so the whole-job
     # throughput is quoted in 256x128x128-equivalent design iterations (iterations/s x dof / 12.83 M dof)
     iters_per_sec = K / (total_ms * 1e-3)
-    dof_scale = chain.ndof_global / (3 * 257 * 129 * 129) if world > 1 else 1.0
+    dof_scale = chain.ndof_global / (3 * 257 * 129 * 129) if (world > 1 and args.problem == "cantilever") else 1.0
     value = iters_per_sec * dof_scale
     compl = [float(c) for c in compl]
 
@@ -382,7 +391,7 @@ def run_b200(args, full):
     traffic = 8.5216e9 + 0.0906e9 if (tuple(full) == (256, 128, 128) and world == 1) else None
     step_avg_ms = total_ms / K
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "tile_kernel<3,JACOBI> on the finest assembled matrix", "kernel_ms": kern_ms,
+                "kernel": f"tile_kernel<{A.grid.ndof},JACOBI> on the finest assembled matrix", "kernel_ms": kern_ms,
                 "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "reference_layout_gbs": (12 * nnz + 4 * (n + 1) + 40 * n) / (kern_ms * 1e-3) / 1e9,
                 "fine_level_operator_launches_per_step": (fine_csr + fine_mf) / K,
@@ -410,8 +419,9 @@ def run_b200(args, full):
     matrix_free = None
     if was_mf:
         mf_ms = time_sweeps()
-        flops = 2.0 * 600 * (n / 3)  # 8 elements x (72 + 3) FMA per node
-        matrix_free = {"kernel": "elem_kernel<3,3D,JACOBI> (finest level from element densities)", "kernel_ms": mf_ms,
+        ndof_ = A.grid.ndof
+        flops = 2.0 * 8 * (8 * ndof_ * ndof_ + ndof_) * (n / ndof_)  # 8 elements x (8 nodes x ndof^2 + ndof) FMA per node
+        matrix_free = {"kernel": f"elem_kernel<{A.grid.ndof},3D,JACOBI> (finest level from element densities)", "kernel_ms": mf_ms,
                        "bound": "fp64 pipe", "fp64_tflops": flops / (mf_ms * 1e-3) / 1e12, "dram_bytes_algorithmic": 40 * n + 8 * nel,
                        "launches_per_step": fine_mf / K, "share_of_step": (fine_mf / K) * mf_ms / step_avg_ms,
                        "speedup_vs_streaming_assembled_values": kern_ms / mf_ms,
@@ -454,7 +464,8 @@ def run_b200(args, full):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"3D cantilever compliance {full[0]}x{full[1]}x{full[2]} hex8 ({chain.ndof_global} dof, "
+            "config": {"workload": f"3D {'cantilever compliance' if args.problem == 'cantilever' else 'heat-sink (scalar conduction) compliance'} "
+                                   f"{full[0]}x{full[1]}x{full[2]} hex8 ({chain.ndof_global} dof, "
                                    f"{n} dof / nnz {nnz} per GPU), "
                                    f"SIMP p=3 xmin=1e-9, DensityFilter r=2, LDAS+CG(tol 1e-8)+GMG({len(chain.mgs)} levels, "
                                    "5+5 Jacobi w=0.5), warm start, seeded design perturbations; finest-level operator " +

@@ -19,9 +19,9 @@ enum { MODE_SPMV = PMB_SPMV, MODE_RESID = PMB_RESIDUAL, MODE_JACOBI = PMB_JACOBI
 
 // T nodes per tile, PARTS threads per node, STAGES ring slots; NT = threads per CTA rounded up to whole warps;
 // TILE_DOUBLES = largest staged run (+2 for the 16-byte alignment slack), itself kept a multiple of 2.
-template <int NDOF, int T_, int PARTS_, int STAGES_>
+template <int NDOF, int T_, int PARTS_, int STAGES_, int CTAS_>
 struct TileCfgBase {
-  static constexpr int T = T_, PARTS = PARTS_, STAGES = STAGES_;
+  static constexpr int T = T_, PARTS = PARTS_, STAGES = STAGES_, CTAS = CTAS_;  // CTAS = resident CTAs per SM
   static constexpr int NT = (T_ * PARTS_ + 31) / 32 * 32;
   static constexpr int TILE_DOUBLES = (T_ * NDOF * NDOF * 27 + 2 + 1) / 2 * 2;
   static constexpr size_t SMEM_BYTES = sizeof(double) * TILE_DOUBLES * STAGES_;
@@ -29,16 +29,15 @@ struct TileCfgBase {
 template <int NDOF>
 struct TileCfg;
 template <>
-struct TileCfg<3> : TileCfgBase<3, 16, 9, 3> {};
+struct TileCfg<3> : TileCfgBase<3, 16, 9, 3, 2> {};
 template <>
-struct TileCfg<2> : TileCfgBase<2, 48, 3, 2> {};
+struct TileCfg<2> : TileCfgBase<2, 48, 3, 2, 2> {};
 template <>
-struct TileCfg<1> : TileCfgBase<1, 96, 3, 3> {};
+struct TileCfg<1> : TileCfgBase<1, 96, 3, 2, 4> {};  // small tiles: more CTAs in flight hide the per-tile latency
 
-static constexpr int CTAS_PER_SM = 2;
 
 template <int NDOF, int MODE>
-__global__ void __launch_bounds__(TileCfg<NDOF>::NT, CTAS_PER_SM)
+__global__ void __launch_bounds__(TileCfg<NDOF>::NT, TileCfg<NDOF>::CTAS)
     tile_kernel(Geo g, int ntiles, int tiles_per_row, int stream_hint, const double* __restrict__ A,
                 const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ diag, double w,
                 double* __restrict__ y, const double* __restrict__ dotv, double* __restrict__ partials,
@@ -224,14 +223,14 @@ static int tiles_per_row(const Geo& g) { return (g.NX + TileCfg<NDOF>::T - 1) / 
 template <int NDOF>
 static long long tile_count(const Geo& g) { return (long long)tiles_per_row<NDOF>(g) * g.NY * g.nzl; }
 
-static int grid_for(long long ntiles) {
-  long long cap = (long long)sm_count() * CTAS_PER_SM;
+static int grid_for(long long ntiles, int ctas_per_sm) {
+  long long cap = (long long)sm_count() * ctas_per_sm;
   return (int)(ntiles < cap ? ntiles : cap);
 }
 
 extern "C" long long pmb_spmv_ws_doubles(const pmb_grid* p) {
   if (validate_grid(p, "pmb_spmv_ws_doubles")) return -1;
-  return 3LL * sm_count() * CTAS_PER_SM;
+  return 3LL * sm_count() * 4;  // largest resident-CTA count of any configuration
 }
 
 template <int NDOF, int MODE>
@@ -246,7 +245,7 @@ static int launch_tile(const Geo& g, const double* A, const double* x, const dou
   }
   const long long ntiles = tile_count<NDOF>(g);
   PMB_REQUIRE(ntiles < 2147483647LL, "pmb_spmv: too many tiles");
-  const int grid = grid_for(ntiles);
+  const int grid = grid_for(ntiles, Cfg::CTAS);
   // matrices that do not fit in L2 anyway are streamed evict-first so the x / b / y vectors keep their lines
   const long long nnz_bytes = 8LL * NDOF * NDOF * (pre1(g.kz0 + g.nzl, g.NZ) * g.Sy * g.Sx - g.bo0);
   const int stream_hint = nnz_bytes > (96LL << 20);
