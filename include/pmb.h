@@ -72,8 +72,9 @@ int pmb_csr_pattern(const pmb_grid* g, void* indptr, void* indices, int index_bi
 
 /* K1: data = sum_e x_e Ke (sequential adds from 0.0 in ascending element number, no FMA: bit-exact with
  * np.add.at), rows/cols in bcmask (1 byte per dof, may be NULL) zeroed, bc diagonal = bcdiagval.
- * x points at element layer kz0 (layer kz0-1 is read as halo when kz0 > 0). Ke is (nn*ndof)^2 row-major. */
-int pmb_assemble(const pmb_grid* g, const double* Ke, const double* x, const unsigned char* bcmask,
+ * x points at element layer kz0 (layer kz0-1 is read as halo when kz0 > 0). Ke is (nn*ndof)^2 row-major and a HOST
+ * pointer (it is passed to the kernel through the parameter constant bank). */
+int pmb_assemble(const pmb_grid* g, const double* Ke_host, const double* x, const unsigned char* bcmask,
                  double bcdiagval, double* data, void* stream);
 
 /* K11: dx_e = sum_{a,b} u[dof(e,a)] Ke[a,b] v[dof(e,b)], u and v taken as 0 at masked dofs.

@@ -146,7 +146,7 @@ class AssembleGeneral(Module):
         if self._mat is None:
             self._mat = DeviceCSR(self.grid, bc_mask=self._bcmask, comm=self._ctx.comm, level=0)
         mat = self._mat
-        _lib.call("pmb_assemble", self.grid, dv.ptr(self._Ke_dev), dv.ptr(x), dv.ptr(self._bcmask),
+        _lib.call("pmb_assemble", self.grid, self._Ke_host.ctypes.data, dv.ptr(x), dv.ptr(self._bcmask),
                   float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
         mat.invalidate()
         mat.generator = dict(ke=self._Ke_host, s=x, mask=self._bcmask,

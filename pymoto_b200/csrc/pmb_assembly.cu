@@ -53,98 +53,163 @@ extern "C" int pmb_csr_pattern(const pmb_grid* p, void* indptr, void* indices, i
 }
 
 // ------------------------------------------------------------------------------------------------- K1
-// One thread per (node, neighbour slot): the NDOF x NDOF block A[n, c] (NDOF runs of NDOF consecutive CSR entries).
-template <int NDOF>
-__global__ void __launch_bounds__(256) assemble_kernel(Geo g, const double* __restrict__ Ke, const double* __restrict__ x,
-                                                        const unsigned char* __restrict__ bcmask, double bcdiagval,
-                                                        double* __restrict__ data) {
-  __shared__ double sKe[8 * NDOF * 8 * NDOF];
-  const int nn = g.dim3 ? 8 : 4;
-  const int ke_ld = nn * NDOF;
-  for (int q = threadIdx.x; q < ke_ld * ke_ld; q += blockDim.x) sKe[q] = Ke[q];
-  __syncthreads();
+// A CTA builds the CSR values of T consecutive nodes of one x-row -- ONE contiguous run of the data array -- in shared
+// memory and writes it out with fully coalesced stores.  One thread per (node, z-plane of neighbours): all element /
+// local-node / dof indices are compile-time after unrolling, so the element matrix is read from the kernel-parameter
+// constant bank and the only run-time quantities are the <= 8 element scalings, the Dirichlet mask and the slot
+// offsets of boundary nodes.  Every entry is the sum of its element contributions in ascending element number with a
+// separate multiply and add (no FMA): the order and rounding of np.add.at (assembly.py:267-268) -> bit-identical.
+// (Elements outside the grid enter with scaling +0.0: x + (+-0.0) == x for every x the sum can hold, so the result
+// does not change.)
+template <int NDOF, bool DIM3>
+struct AsmKe {
+  static constexpr int NN = DIM3 ? 8 : 4;
+  static constexpr int LD = NN * NDOF;
+  double v[LD * LD];
+};
 
-  // 3-D launch: blockIdx.y = j, blockIdx.z = owned plane, blockIdx.x * 256 + threadIdx.x = i * 27 + slot.  All index
-  // arithmetic below is 32-bit without runtime divisions (the kernel is instruction-bound, not bandwidth-bound, otherwise)
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= g.NX * 27) return;
-  const int i = q / 27, s = q - i * 27;
-  const int j = blockIdx.y, k = g.kz0 + blockIdx.z;
-  const long long ln = ((long long)blockIdx.z * g.NY + j) * g.NX + i;
-  int dk = s / 9 - 1, dj = (s / 3) % 3 - 1, di = s % 3 - 1;
-  int ci = i + di, cj = j + dj, ck = k + dk;
-  if (ci < 0 || ci >= g.NX || cj < 0 || cj >= g.NY || ck < 0 || ck >= g.NZ) return;
-  int cx = cnt1(i, g.NX), cy = cnt1(j, g.NY), cz = cnt1(k, g.NZ);
-  int ilo = max(i - 1, 0), jlo = max(j - 1, 0), klo = max(k - 1, 0);
-  long long L = (long long)cx * cy * cz * NDOF;
-  int nbr = ((ck - klo) * cy + (cj - jlo)) * cx + (ci - ilo);
-  long long off = (long long)(NDOF * NDOF) * (block_offset(g, i, j, k) - g.bo0) + (long long)nbr * NDOF;
-
-  // local (slab-relative) node numbers for the bc mask: row node ln, column node lc (may lie in a halo plane)
-  long long lc = ((long long)(ck - g.kz0) * g.NY + cj) * g.NX + ci;
-
-  double acc[NDOF][NDOF];
+// the part of one node's block row that couples to the neighbour plane k + DK (DK compile-time)
+template <int NDOF, bool DIM3, int DK>
+__device__ __forceinline__ void assemble_node_plane(const Geo& g, const AsmKe<NDOF, DIM3>& ke, const double* __restrict__ x,
+                                                    const unsigned char* __restrict__ bcmask, double bcdiagval, double* nodep,
+                                                    int i, int j, int k, int kl, int cy, int cz, int jlo, int klo) {
+  constexpr int LD = AsmKe<NDOF, DIM3>::LD;
+  const int ck = k + DK;
+  if (ck < 0 || ck >= g.NZ) return;
+  const int cx = cnt1(i, g.NX), ilo = max(i - 1, 0);
+  const int L = cx * cy * cz * NDOF;
+  const long long ln = ((long long)kl * g.NY + j) * g.NX + i;
+  // element scalings of the (up to) 8 elements around the node; absent elements count as +0.0
+  double xe[2][2][2];
 #pragma unroll
-  for (int d = 0; d < NDOF; ++d)
+  for (int oz = 0; oz < (DIM3 ? 2 : 1); ++oz)
 #pragma unroll
-    for (int cd = 0; cd < NDOF; ++cd) acc[d][cd] = 0.0;
-
-  const int nzo = g.dim3 ? 2 : 1;
-  for (int oz = 0; oz < nzo; ++oz) {
-    int ek = g.dim3 ? (k - 1 + oz) : 0;
-    int az = g.dim3 ? (1 - oz) : 0;
-    int bz = az + dk;
-    if (ek < 0 || ek >= g.nzE || bz < 0 || bz > (g.dim3 ? 1 : 0)) continue;
-    for (int oy = 0; oy < 2; ++oy) {
-      int ej = j - 1 + oy, ay = 1 - oy, by = ay + dj;
-      if (ej < 0 || ej >= g.ny || by < 0 || by > 1) continue;
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
       for (int ox = 0; ox < 2; ++ox) {
-        int ei = i - 1 + ox, ax = 1 - ox, bx = ax + di;
-        if (ei < 0 || ei >= g.nx || bx < 0 || bx > 1) continue;
+        const int ei = i - 1 + ox, ej = j - 1 + oy, ek = DIM3 ? k - 1 + oz : 0;
+        const bool in = ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE;
         // element layer index relative to the slab's first owned layer (layer kz0); kz0-1 is the halo
-        long long e = ((long long)(ek - g.kz0) * g.ny + ej) * g.nx + ei;
-        double xe = __ldg(x + e);
-        int a = ax + 2 * ay + 4 * az, b = bx + 2 * by + 4 * bz;
-        const double* kp = sKe + (a * NDOF) * ke_ld + b * NDOF;
-        // ascending element number, separate multiply and add: the order and rounding of np.add.at (assembly.py:267-268)
-#pragma unroll
-        for (int d = 0; d < NDOF; ++d)
-#pragma unroll
-          for (int cd = 0; cd < NDOF; ++cd) acc[d][cd] = __dadd_rn(acc[d][cd], __dmul_rn(kp[d * ke_ld + cd], xe));
+        xe[oz][oy][ox] = in ? __ldg(x + ((long long)(ek - (DIM3 ? g.kz0 : 0)) * g.ny + ej) * g.nx + ei) : 0.0;
       }
+  bool rowbc[NDOF];
+#pragma unroll
+  for (int d = 0; d < NDOF; ++d) rowbc[d] = bcmask && bcmask[ln * NDOF + d];
+
+#pragma unroll
+  for (int dj = -1; dj <= 1; ++dj) {
+    const int cj = j + dj;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+      const int ci = i + di;
+      if (cj < 0 || cj >= g.NY || ci < 0 || ci >= g.NX) continue;
+      const int nbr = ((ck - klo) * cy + (cj - jlo)) * cx + (ci - ilo);
+      const long long lc = ((long long)(ck - g.kz0) * g.NY + cj) * g.NX + ci;  // may lie in a halo plane
+      bool colbc[NDOF];
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) colbc[c] = bcmask && bcmask[lc * NDOF + c];
+      constexpr bool zself = (DK == 0);
+      const bool self = zself && di == 0 && dj == 0;
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          double acc = 0.0;
+          // elements in ascending number (oz, oy, ox); every Ke index below is a compile-time constant
+#pragma unroll
+          for (int oz = 0; oz < (DIM3 ? 2 : 1); ++oz) {
+            const int az = DIM3 ? 1 - oz : 0, bz = az + DK;
+            if (bz < 0 || bz > (DIM3 ? 1 : 0)) continue;
+#pragma unroll
+            for (int oy = 0; oy < 2; ++oy) {
+              const int ay = 1 - oy, by = ay + dj;
+              if (by < 0 || by > 1) continue;
+#pragma unroll
+              for (int ox = 0; ox < 2; ++ox) {
+                const int ax = 1 - ox, bx = ax + di;
+                if (bx < 0 || bx > 1) continue;
+                const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+                acc = __dadd_rn(acc, __dmul_rn(ke.v[(a * NDOF + d) * LD + bn * NDOF + c], xe[oz][oy][ox]));
+              }
+            }
+          }
+          double v = acc;
+          if (rowbc[d] || colbc[c]) v = (self && c == d) ? bcdiagval : 0.0;
+          nodep[d * L + nbr * NDOF + c] = v;
+        }
     }
   }
-  bool rowbc[NDOF], colbc[NDOF];
-#pragma unroll
-  for (int d = 0; d < NDOF; ++d) {
-    rowbc[d] = bcmask && bcmask[ln * NDOF + d];
-    colbc[d] = bcmask && bcmask[lc * NDOF + d];
-  }
-#pragma unroll
-  for (int d = 0; d < NDOF; ++d)
-#pragma unroll
-    for (int cd = 0; cd < NDOF; ++cd) {
-      double v = acc[d][cd];
-      if (rowbc[d] || colbc[cd]) v = (lc == ln && cd == d) ? bcdiagval : 0.0;
-      data[off + d * L + cd] = v;
-    }
 }
 
-extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke, const double* x, const unsigned char* bcmask,
-                            double bcdiagval, double* data, void* stream) {
-  if (validate_grid(p, "pmb_assemble")) return 1;
-  PMB_REQUIRE(Ke && x && data, "pmb_assemble: NULL pointer argument");
-  Geo g = make_geo(p);
-  PMB_REQUIRE(g.NY <= 65535 && g.nzl <= 65535, "pmb_assemble: grid too large for the 3-D launch");
-  dim3 blocks((g.NX * 27 + 255) / 256, g.NY, g.nzl);
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (g.ndof) {
-    case 1: assemble_kernel<1><<<blocks, 256, 0, st>>>(g, Ke, x, bcmask, bcdiagval, data); break;
-    case 2: assemble_kernel<2><<<blocks, 256, 0, st>>>(g, Ke, x, bcmask, bcdiagval, data); break;
-    case 3: assemble_kernel<3><<<blocks, 256, 0, st>>>(g, Ke, x, bcmask, bcdiagval, data); break;
+template <int NDOF, bool DIM3>
+__global__ void __launch_bounds__(DIM3 ? 96 : 32) assemble_kernel(Geo g, const __grid_constant__ AsmKe<NDOF, DIM3> ke,
+                                                                  const double* __restrict__ x,
+                                                                  const unsigned char* __restrict__ bcmask, double bcdiagval,
+                                                                  double* __restrict__ data) {
+  constexpr int T = 32, PARTS = DIM3 ? 3 : 1, NT = T * PARTS;
+  extern __shared__ double tile[];  // T * NDOF * NDOF * 27 doubles
+  const int tid = threadIdx.x;
+  const int gI = tid % T, part = tid / T;  // part = neighbour z-plane (dk = part - 1) in 3-D: uniform per warp
+  const int i0 = blockIdx.x * T, j = blockIdx.y, kl = blockIdx.z, k = g.kz0 + kl;
+  const int ni = min(T, g.NX - i0);
+  const int cy = cnt1(j, g.NY), cz = cnt1(k, g.NZ);
+  const int jlo = max(j - 1, 0), klo = max(k - 1, 0);
+  const long long per = (long long)(NDOF * NDOF) * cy * cz;
+  const long long rowbase = pre1(k, g.NZ) * g.Sy * g.Sx + (long long)cz * (pre1(j, g.NY) * g.Sx) - g.bo0;
+  const long long e0 = (long long)(NDOF * NDOF) * rowbase + per * pre1(i0, g.NX);
+  const int nelem = (int)(per * (pre1(i0 + ni, g.NX) - pre1(i0, g.NX)));
+  if (gI < ni) {
+    const int i = i0 + gI;
+    double* nodep = tile + per * (pre1(i, g.NX) - pre1(i0, g.NX));
+if (!DIM3 || part == 1) assemble_node_plane<NDOF, DIM3, 0>(g, ke, x, bcmask, bcdiagval, nodep, i, j, k, kl, cy, cz, jlo, klo);
+    else if (part == 0) assemble_node_plane<NDOF, DIM3, -1>(g, ke, x, bcmask, bcdiagval, nodep, i, j, k, kl, cy, cz, jlo, klo);
+    else assemble_node_plane<NDOF, DIM3, 1>(g, ke, x, bcmask, bcdiagval, nodep, i, j, k, kl, cy, cz, jlo, klo);
   }
+  __syncthreads();
+  // coalesced write-out of the contiguous run
+  for (int q = tid; q < nelem; q += NT) data[e0 + q] = tile[q];
+}
+
+template <int NDOF, bool DIM3>
+static int launch_assemble(const Geo& g, const double* Ke_host, const double* x, const unsigned char* bcmask, double bcdiagval,
+                           double* data, cudaStream_t st) {
+  AsmKe<NDOF, DIM3> ke;
+  memcpy(ke.v, Ke_host, sizeof(ke.v));
+  constexpr int T = 32, NT = DIM3 ? 96 : 32;
+  const size_t smem = sizeof(double) * T * NDOF * NDOF * 27;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(assemble_kernel<NDOF, DIM3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pmb_set_error("assemble_kernel attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 blocks((g.NX + T - 1) / T, g.NY, g.nzl);
+  assemble_kernel<NDOF, DIM3><<<blocks, NT, smem, st>>>(g, ke, x, bcmask, bcdiagval, data);
   PMB_CHECK_LAUNCH("pmb_assemble");
   return 0;
+}
+
+extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke_host, const double* x, const unsigned char* bcmask,
+                            double bcdiagval, double* data, void* stream) {
+  if (validate_grid(p, "pmb_assemble")) return 1;
+  PMB_REQUIRE(Ke_host && x && data, "pmb_assemble: NULL pointer argument");
+  Geo g = make_geo(p);
+  PMB_REQUIRE(g.NY <= 65535 && g.nzl <= 65535, "pmb_assemble: grid too large for the 3-D launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g.dim3) {
+    switch (g.ndof) {
+      case 1: return launch_assemble<1, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 2: return launch_assemble<2, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 3: return launch_assemble<3, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+    }
+  } else {
+    switch (g.ndof) {
+      case 1: return launch_assemble<1, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 2: return launch_assemble<2, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 3: return launch_assemble<3, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+    }
+  }
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------- K11
