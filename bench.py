@@ -315,9 +315,13 @@ def run_b200(args, full):
     compl = [float(c) for c in compl]
 
     if args.profile:
+        from pymoto_b200.solvers import GeometricMultigrid as _GMG
+
+        graphs, _GMG.use_cuda_graph = _GMG.use_cuda_graph, False  # time every call individually
         _lib.profile_times = {}
         chain.step(xs_dev[W + K])
         prof, _lib.profile_times = _lib.profile_times, None
+        _GMG.use_cuda_graph = graphs
         tot = sum(v[1] for v in prof.values())
         if rank == 0:
             print(f"# per-call breakdown of one step (synchronised calls), total {tot:.2f} ms", file=sys.stderr)
@@ -475,7 +479,8 @@ def run_b200(args, full):
                                    f"{full[0]}x{full[1]}x{full[2]} hex8 ({chain.ndof_global} dof, "
                                    f"{n} dof / nnz {nnz} per GPU), "
                                    f"SIMP p=3 xmin=1e-9, DensityFilter r=2, LDAS+CG(tol 1e-8)+GMG({len(chain.mgs)} levels, "
-                                   "5+5 Jacobi w=0.5), warm start, seeded design perturbations; finest-level operator " +
+                                   "5+5 Jacobi w=0.5, V-cycle replayed as one CUDA graph on 1 GPU), warm start, seeded design perturbations; "
+                                   "finest-level operator " +
                                    ("matrix-free (element-wise)" if not args.csr else "streamed from the assembled CSR values"),
                        "l2": "inputs larger than L2 (matrix values 8*nnz bytes per level-0 sweep)",
                        "parallelism": "1 GPU" if world == 1 else

@@ -53,6 +53,7 @@ class DeviceCSR:
         self.bc_mask = bc_mask  # uint8 per dof or None (set by the assembly module; informational)
         self._indptr = self._indices = None
         self._diag = self._nnz_off = None
+        self._diag_buf = self._nnz_off_buf = None
         self._entry_offsets = {}
         self.generator = None  # dict(ke=host ndarray, s=device tensor, mask=device uint8 or None, bcdiag=float)
 
@@ -108,8 +109,10 @@ class DeviceCSR:
     # ---- row statistics: diagonal + number of non-zero off-diagonals, one pass over the values
     def rowstats(self):
         if self._diag is None:
-            self._diag = dv.empty(self.n)
-            self._nnz_off = dv.empty(self.n, torch.int32)
+            if self._diag_buf is None:  # persistent storage: addresses stay fixed across updates (CUDA-graph replays rely on it)
+                self._diag_buf = dv.empty(self.n)
+                self._nnz_off_buf = dv.empty(self.n, torch.int32)
+            self._diag, self._nnz_off = self._diag_buf, self._nnz_off_buf
             _lib.call("pmb_rowstats", self.grid, dv.ptr(self._buf), dv.ptr(self._diag), dv.ptr(self._nnz_off), dv.stream())
         return self._diag, self._nnz_off
 

@@ -14,6 +14,7 @@ vectors inside the solvers are CUDA tensors; ``solve`` accepts numpy arrays or C
 kind.  The matrices are :class:`DeviceCSR` (real, symmetric), so ``trans`` in {"N", "T", "H"} all solve the same
 system; anything else raises ``TypeError`` like the reference.
 """
+import os
 import time
 import warnings
 
@@ -151,6 +152,10 @@ class GeometricMultigrid(Preconditioner):
     """
 
     _available_cycles = ["v", "w"]
+    # Replay the whole V-cycle (all levels, ~70 kernel launches) as ONE CUDA graph when it is used as a preconditioner on
+    # a single GPU.  Every buffer the cycle touches is persistent, so the graph is captured once per hierarchy and only
+    # re-captured if an address changes.  PMB_CUDA_GRAPH=0 disables it.
+    use_cuda_graph = os.environ.get("PMB_CUDA_GRAPH", "1") != "0"
 
     def __init__(self, domain, A=None, cycle: str = "V", inner_level: LinearSolver = None, smoother: LinearSolver = None,
                  smooth_steps: int = 5):
@@ -170,6 +175,9 @@ class GeometricMultigrid(Preconditioner):
         self._buf = None
         self._fine_key = None
         self._replicate = False
+        self._graph = None
+        self._graph_sig = None
+        self._eager_calls = 0
         super().__init__(A)
 
     def update(self, A):
@@ -229,8 +237,54 @@ class GeometricMultigrid(Preconditioner):
         nc_local = _lib.query("pmb_nrows", self._gc_local)
         self._buf = dict(u=A.new_vec(), u2=A.new_vec(), t=A.new_vec(), rc=dv.empty(nc_local))
 
+    def _signature(self):
+        """Addresses of everything a captured V-cycle reads or writes, down the whole hierarchy."""
+        sig, lvl = [], self
+        while isinstance(lvl, GeometricMultigrid):
+            if lvl.A is None or lvl._buf is None or lvl.A.comm is not None:
+                return None
+            gen = lvl.A.generator if DeviceCSR.matrix_free else None
+            sig += [lvl.A._buf.data_ptr(), lvl.smoother.D.data_ptr(), float(lvl.smoother.w), lvl.smooth_steps,
+                    None if gen is None else (gen["s"].data_ptr(), None if gen["mask"] is None else gen["mask"].data_ptr(),
+                                              gen["bcdiag"], gen["ke"].ctypes.data, gen["ke"].tobytes())]
+            sig += [lvl._buf[k].data_ptr() for k in ("u", "u2", "t", "rc")]
+            lvl = lvl.inner_level
+        if not isinstance(lvl, SolverDenseInverse) or lvl.inv is None:
+            return None
+        return tuple(sig + [lvl.inv.data_ptr(), lvl._out.data_ptr(), lvl.n])
+
     def solve(self, rhs, x0=None, trans="N"):
         _check_trans(trans)
+        if (GeometricMultigrid.use_cuda_graph and x0 is None and dv.is_device(rhs) and self.A is not None
+                and self.A.comm is None and self.A.level == 0 and rhs.numel() == self.A.shape[0]
+                and not torch.cuda.is_current_stream_capturing()):
+            sig = self._signature()
+            if sig is not None:
+                if self._graph is not None and sig != self._graph_sig:
+                    self._graph = None
+                if self._graph is None and self._eager_calls >= 1:  # one eager pass first (lazy kernel attributes etc.)
+                    self._graph_in = dv.empty(self.A.shape[0])
+                    self._graph_in.copy_(rhs.reshape(-1))
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._graph_out = self._solve_eager(self._graph_in, None)
+                    self._graph, self._graph_sig = g, self._signature()
+                if self._graph is not None:
+                    self._graph_in.copy_(rhs.reshape(-1))
+                    self._graph.replay()
+                    _lib.launch_count += self._graph_launches  # the replay launches the same kernels as the eager pass
+                    for key, cnt in self._graph_stats.items():
+                        _lib.call_stats[key] = _lib.call_stats.get(key, 0) + cnt
+                    return self._graph_out
+        self._eager_calls += 1
+        n0, s0 = _lib.launch_count, dict(_lib.call_stats)
+        out = self._solve_eager(rhs, x0)
+        self._graph_launches = _lib.launch_count - n0
+        self._graph_stats = {k: c - s0.get(k, 0) for k, c in _lib.call_stats.items() if c - s0.get(k, 0) > 0}
+        return out
+
+    def _solve_eager(self, rhs, x0):
         b = dv.to_device(rhs).reshape(-1)
         A, D, w = self.A, self.smoother.D, float(self.smoother.w)
         n = A.shape[0]
