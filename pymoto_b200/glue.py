@@ -1,9 +1,10 @@
-"""Device-resident glue for the compliance loop: SIMP interpolation and the compliance inner product.
+"""Device glue for the compliance loop: SIMP interpolation and the compliance inner product.
 
 In the reference these are generic host modules (``MathExpression("xmin + (1-xmin)*inp0^3")``,
-pymoto/modules/generic.py:14-140, and ``EinSum("i,i->")``, :143-226).  They accept numpy arrays (computed with
-numpy, exactly the reference's expressions) or CUDA tensors (computed by libpmb kernels / a device reduction), so
-a design iteration can stay resident in HBM between the filter, the assembly and the solve.
+pymoto/modules/generic.py:14-140, and ``EinSum("i,i->")``, :143-226).  Here they always run on the GPU (libpmb
+kernels / the deterministic device reduction); like every module of this package they accept numpy arrays or CUDA
+tensors and return the kind they were given, so a design iteration can stay resident in HBM between the filter, the
+assembly and the solve.  (The reference's own MathExpression / EinSum remain usable on numpy Signals next to them.)
 """
 import numpy as np
 
@@ -19,43 +20,38 @@ class SIMP(Module):
         self.xmin, self.p = float(xmin), int(p)
 
     def __call__(self, y):
-        self._y = y
-        if not dv.is_device(y):
-            return self.xmin + (1.0 - self.xmin) * y ** self.p
-        s = dv.empty(y.numel())
-        _lib.call("pmb_simp", y.numel(), self.xmin, self.p, dv.ptr(y), dv.ptr(s), dv.stream())
-        return s
+        yd = dv.to_device(y).reshape(-1)
+        self._y = yd
+        s = dv.empty(yd.numel())
+        _lib.call("pmb_simp", yd.numel(), self.xmin, self.p, dv.ptr(yd), dv.ptr(s), dv.stream())
+        return dv.like_input(s, y)
 
     def _sensitivity(self, ds):
-        y = self._y
-        if not dv.is_device(y):
-            return ds * (self.p * (1.0 - self.xmin) * y ** (self.p - 1))
-        dsd = dv.to_device(ds)
-        dy = dv.empty(y.numel())
-        _lib.call("pmb_simp_bwd", y.numel(), self.xmin, self.p, dv.ptr(y), dv.ptr(dsd), dv.ptr(dy), dv.stream())
-        return dy
+        dsd = dv.to_device(ds).reshape(-1)
+        dy = dv.empty(self._y.numel())
+        _lib.call("pmb_simp_bwd", self._y.numel(), self.xmin, self.p, dv.ptr(self._y), dv.ptr(dsd), dv.ptr(dy), dv.stream())
+        return dv.like_input(dy, ds)
 
 
 class Compliance(Module):
-    """c = u . f (``EinSum('i,i->')``); on device the reduction is the deterministic pmb_dots kernel."""
+    """c = u . f (``EinSum('i,i->')``): deterministic device reduction (+ all-reduce over the slabs when distributed)."""
 
     def __call__(self, u, f):
-        self._u, self._f = u, f
         from . import slab
 
         ctx = slab.context()
-        if not dv.is_device(u):
-            if ctx.active:
-                raise TypeError("distributed runs keep nodal vectors on the device")
-            return np.asarray(u) @ (f.cpu().numpy() if dv.is_device(f) else np.asarray(f))
-        return ctx.comm.allreduce_(dv.dots([(u, dv.to_device(f))]))[0]
+        if ctx.active and not dv.is_device(u):
+            raise TypeError("distributed runs keep nodal vectors on the device")
+        self._u, self._f = dv.to_device(u).reshape(-1), dv.to_device(f).reshape(-1)
+        self._host = not dv.is_device(u)
+        c = ctx.comm.allreduce_(dv.dots([(self._u, self._f)]))[0]
+        return float(c.item()) if self._host else c
 
     def _sensitivity(self, dc):
-        u, f = self._u, self._f
-        if not dv.is_device(u):
-            dc = float(dc)
-            return dc * np.asarray(f), dc * np.asarray(u)
-        fd = dv.to_device(f)
-        if dv.is_device(dc):
-            return dc * fd, dc * u
-        return float(dc) * fd, float(dc) * u
+        dcv = float(dc.item()) if dv.is_device(dc) else float(dc)
+        du, df = dv.empty(self._u.numel()), dv.empty(self._u.numel())
+        dv.lincomb(du, dcv, self._f)
+        dv.lincomb(df, dcv, self._u)
+        if self._host:
+            return du.cpu().numpy(), df.cpu().numpy()
+        return du, df
