@@ -338,13 +338,16 @@ def run_b200(args, full):
             chain.step(pinned[i].to("cuda", non_blocking=True))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = []
         e0.record()
         for i in range(K):
+            t_step = time.perf_counter()
             xd = pinned[W + i].to("cuda", non_blocking=True)
             c, dx = chain.step(xd)
             out_pinned.copy_(dx, non_blocking=True)
             c_pinned.copy_(c.reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the user reads the result on the host every step
+            e2e_steps.append(1e3 * (time.perf_counter() - t_step))
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -353,7 +356,7 @@ def run_b200(args, full):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         e2e = {"value": dof_scale * K / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * nel * world,
-               "d2h_bytes_per_step": (8 * nel + 8) * world}
+               "d2h_bytes_per_step": (8 * nel + 8) * world, "ms_per_step_list": e2e_steps}
 
     # ---------------- roofline.  Two kernels carry the step:
     #  (1) the HBM-bound stencil-CSR kernel (tile_kernel, fused Jacobi sweep): timed on the finest ASSEMBLED matrix
