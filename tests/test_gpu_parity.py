@@ -679,3 +679,40 @@ def test_oc_update_and_minimize_oc_vs_reference(pmb):
     # minimize_oc runs to its stopping criterion on a small problem
     oc2 = pmb.minimize_oc(sx, sc, function=fn, maxit=3, verbosity=0)
     assert oc2.iter <= 3
+
+
+def test_linsolve_multiple_rhs_and_finite_difference(pmb):
+    """reference tests/test_linsolve_sparse.py:32-91 style: K u = f for a block of right-hand sides (solved one by one
+    through LDAS: the second, linearly dependent column costs no CG) and a finite-difference check of d(f.u)/dx."""
+    import scipy.sparse.linalg as spla
+
+    nx, ny, nz = 6, 4, 4
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    P = ComplianceProblem(Grid(nx, ny, nz), kind="cantilever", tol=1e-10, min_size=2)
+    rng = np.random.default_rng(4)
+    x = rng.random(dom.nel) * 0.8 + 0.2
+    asm = pmb.AssembleStiffness(dom, bc=P.bc)
+    mgs = pmb.solvers.auto_multigrid(dom, min_size=2)
+    cg = pmb.solvers.CG(preconditioner=mgs[0], tol=1e-11)
+    ls = pmb.LinSolve(hermitian=True, solver=cg)
+    F = np.stack([P.f, 2.5 * P.f, rng.standard_normal(P.f.size)], axis=1)
+    F[P.bc, 2] = 0.0
+    K = asm(x)
+    U = ls(K, F)
+    assert U.shape == F.shape
+    Ks = K.tocsr().tocsc()
+    for c in range(3):
+        np.testing.assert_allclose(U[:, c], spla.spsolve(Ks, F[:, c]), rtol=0, atol=1e-8 * np.abs(U[:, c]).max())
+    assert len(ls.solver.x_stored) == 2  # column 1 = 2.5 x column 0 came from the LDAS database
+    # finite differences of c(x) = f . u(x) against the analytical sensitivity -lam_e^T Ke u_e (single rhs)
+    ls1 = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=pmb.solvers.auto_multigrid(dom, min_size=2)[0], tol=1e-12))
+    u = ls1(asm(x), P.f)
+    c0 = u @ P.f
+    dmat, _ = ls1._sensitivity(P.f)
+    dcdx = asm._sensitivity(dmat)[0]
+    for e in rng.integers(0, dom.nel, 5):
+        xp = x.copy()
+        xp[e] += 1e-6
+        lsp = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=pmb.solvers.auto_multigrid(dom, min_size=2)[0], tol=1e-12))
+        cp = lsp(asm(xp), P.f) @ P.f
+        assert abs((cp - c0) / 1e-6 - dcdx[e]) <= 2e-4 * abs(dcdx[e]) + 1e-7
