@@ -16,4 +16,4 @@ Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified r
 (tests/test_assembly.py, tests/test_solvers_multigrid.py, tests/test_domain.py).
 """
 from .grid import Grid  # noqa: F401
-from . import assembly, filter, solvers, chain  # noqa: F401
+from . import assembly, filter, solvers, chain, nextrows  # noqa: F401
