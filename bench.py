@@ -140,41 +140,100 @@ def run_reference(args, full):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region.  Primary: NVML polled in-process every 5 ms (the timed
+    region is a few hundred ms, too short for a freshly spawned ``nvidia-smi -lms`` to report anything); fallback: an
+    ``nvidia-smi`` poller that must be started before the warm-up.  Only samples stamped inside [begin(), end()] count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.proc, self.nvml, self.h = gpu_index, [], None, None, None
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.gpu]) if self.gpu < len(ids) else self.gpu
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
     def start(self):
+        """Call BEFORE the warm-up steps."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.nvml, self.h = self._nvml_handle()
+            self.max_sm = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = ((n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (n.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, self.max_sm, [nm for b, nm in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit() and r[2].replace(".", "").isdigit():
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                  [nm for nm, v in zip(self.NAMES, r[5:9]) if v.lower().startswith("active")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi on this host"], "samples": 0}
         self.t.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nme, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t0 = self.t0 if self.t0 is not None else -1e300
+        t1 = self.t1 if self.t1 is not None else 1e300
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        scope = "timed region"
+        if not rows:  # poller too slow for the region: fall back to everything since start() (warm-up included) and say so
+            rows, scope = list(self.rows), "warm-up + timed region"
+        reasons = sorted({nm for r in rows for nm in r[3]})
+        return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None,
+                "sm_max_mhz": max(r[2] for r in rows) if rows else None, "reasons": reasons, "samples": len(rows),
+                "source": self.source, "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -282,11 +341,12 @@ def run_b200(args, full):
         torch.cuda.synchronize()
         return
     # ---------------- device-resident timing
-    for i in range(W):
-        chain.step(xs_dev[i])
     sampler = ClockSampler(local)
     sampler.start()
+    for i in range(W):
+        chain.step(xs_dev[i])
     barrier()
+    sampler.begin()
     launches0 = _lib.launch_count
     stats0 = dict(_lib.call_stats)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
@@ -298,6 +358,7 @@ def run_b200(args, full):
         cg_its.append(chain.cg.iterations)
         compl.append(c)
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     launches = _lib.launch_count - launches0
     stats = {k: v - stats0.get(k, 0) for k, v in _lib.call_stats.items() if v - stats0.get(k, 0) > 0}
