@@ -151,6 +151,7 @@ class AssembleGeneral(Module):
         mat.invalidate()
         mat.generator = dict(ke=self._Ke_host, s=x, mask=self._bcmask,
                              bcdiag=float(self.bcdiagval if self.bcdiagval is not None else 0.0))
+        mat.autotune_matrix_free()
         return mat
 
     def _sensitivity(self, dgdmat):

@@ -11,6 +11,7 @@
 // One thread per node: the masked x of the node's 27-neighbourhood and the densities of its 8 (4) elements are staged
 // in a shared-memory brick, the element matrix lives in the kernel-parameter constant bank so every FMA takes its
 // Ke operand straight from c[0x0][...] (compile-time indices after full unrolling).
+#include <cstdlib>
 #include "pmb_tilestream.cuh"
 
 enum { EMODE_SPMV = PMB_SPMV, EMODE_RESID = PMB_RESIDUAL, EMODE_JACOBI = PMB_JACOBI };
@@ -193,17 +194,230 @@ __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variant 2 (3-D only): NPT nodes per thread, stacked along z.  The kernel above issues ~3.1 instructions per DFMA
+// (one LDCU.128 of two Ke constants per two DFMAs, 81 LDS per node, staging and epilogue per node), so the issue
+// slots -- not the FP64 pipe (one warp DFMA per 2 cycles per SM sub-partition) -- bound it.  Stacking NPT nodes per
+// thread lets every uniform-register load of a Ke constant feed NPT DFMAs and amortises the staging of the brick
+// apron over a larger brick.  Epilogue operands are loaded after the FMA phase to keep the
+// 24 NPT accumulators in registers.  Same arithmetic per node in the same order, so both variants give identical y
+// (the fused dot-product partials are grouped differently).
+// ---------------------------------------------------------------------------------------------------------
+template <int NDOF, int MODE, int BY, int BZT, int NPT, int MINB>
+__global__ void __launch_bounds__(32 * BY * BZT, MINB)
+    elem_kernel_v2(Geo g, const __grid_constant__ KeParam<NDOF, true> ke, const double* __restrict__ s,
+                   const unsigned char* __restrict__ mask, double bcdiag, const double* __restrict__ x,
+                   const double* __restrict__ b, const double* __restrict__ diag, double w, double* __restrict__ y,
+                   const double* __restrict__ dotv, double* __restrict__ partials) {
+  constexpr int NT = 32 * BY * BZT;
+  constexpr int BX = 32, BZ = BZT * NPT;
+  constexpr int TX = BX + 2, TY = BY + 2, TZ = BZ + 2;
+  constexpr int SZ = BZ + 1;
+  constexpr int LD = KeParam<NDOF, true>::LD;
+  constexpr int ROWLEN = TX * NDOF;
+  constexpr int RP = NT / 128;  // brick rows staged per pass (128 threads each)
+  static_assert(NT % 128 == 0 && ROWLEN <= 128, "staging layout");
+  __shared__ double su[TZ][TY][ROWLEN];
+  __shared__ double ss[SZ][BY + 1][BX + 1];
+  __shared__ double wred[3][NT / 32];
+
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, kl0 = blockIdx.z * BZ;
+  const long long safe = (((long long)kl0 * g.NY + j0) * g.NX + i0) * NDOF;  // first dof of the brick: always owned
+  {
+    constexpr int NROW = TZ * TY, NQ = (NROW + RP - 1) / RP;
+    const int col = tid & 127, sub = tid >> 7;
+    const int i = i0 - 1 + col / NDOF;
+    const bool colin = col < ROWLEN && i >= 0 && i < g.NX;
+    double xv[NQ];
+    unsigned char mk[NQ];
+    bool inb[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int row = RP * q + sub;
+      const int ty = row % TY, tz = row / TY;
+      const int j = j0 - 1 + ty, k = g.kz0 + kl0 - 1 + tz;
+      inb[q] = colin && row < NROW && j >= 0 && j < g.NY && k >= 0 && k < g.NZ && k <= g.kz0 + g.nzl;
+      const long long idx = inb[q] ? (((long long)(k - g.kz0) * g.NY + j) * g.NX + (i0 - 1)) * NDOF + col : safe;
+      xv[q] = __ldg(x + idx);
+      mk[q] = mask ? __ldg(mask + idx) : (unsigned char)0;
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int row = RP * q + sub;
+      if (col < ROWLEN && row < NROW) su[row / TY][row % TY][col] = (inb[q] && !mk[q]) ? xv[q] : 0.0;
+    }
+  }
+  {
+    constexpr int NS = SZ * (BY + 1) * (BX + 1), NQ = (NS + NT - 1) / NT;
+    double sv[NQ];
+    bool sin[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int p = tid + NT * q;
+      const int tx = p % (BX + 1), ty = (p / (BX + 1)) % (BY + 1), tz = p / ((BX + 1) * (BY + 1));
+      const int ei = i0 - 1 + tx, ej = j0 - 1 + ty, ek = g.kz0 + kl0 - 1 + tz;
+      sin[q] = p < NS && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE && ek < g.kz0 + g.nzl;
+      const long long sidx = sin[q] ? ((long long)(ek - g.kz0) * g.ny + ej) * g.nx + ei : 0;
+      sv[q] = __ldg(s + sidx);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int p = tid + NT * q;
+      if (p < NS) ss[p / ((BX + 1) * (BY + 1))][(p / (BX + 1)) % (BY + 1)][p % (BX + 1)] = sin[q] ? sv[q] : 0.0;
+    }
+  }
+  const int tx = tid % BX, ty = (tid / BX) % BY, tzb = (tid / (BX * BY)) * NPT;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool valid_ij = i < g.NX && j < g.NY;
+  __syncthreads();
+
+  constexpr int NE = 8;
+  double t[NPT][NE][NDOF];
+  const bool active = valid_ij && kl0 + tzb < g.nzl;
+  if (active) {
+#pragma unroll
+    for (int p = 0; p < NPT; ++p)
+#pragma unroll
+      for (int e = 0; e < NE; ++e)
+#pragma unroll
+        for (int d = 0; d < NDOF; ++d) t[p][e][d] = 0.0;
+    // same (dk, dj, di) order per node as elem_kernel; the NPT nodes of a thread consume the same Ke constants in the
+    // same step, so one uniform-register load feeds NPT DFMAs
+#pragma unroll
+    for (int dk = -1; dk <= 1; ++dk)
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+          double uv[NPT][NDOF];
+#pragma unroll
+          for (int p = 0; p < NPT; ++p) {
+            const double* up = &su[tzb + p + 1 + dk][ty + 1 + dj][(tx + 1 + di) * NDOF];
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) uv[p][c] = up[c];
+          }
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
+            const int ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
+            const int bx = ax + di, by = ay + dj, bz = az + dk;
+            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
+            const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+              for (int d = 0; d < NDOF; ++d) {
+                const double kv = ke.v[(a * NDOF + d) * LD + bn * NDOF + c];
+#pragma unroll
+                for (int p = 0; p < NPT; ++p) t[p][e][d] = fma(kv, uv[p][c], t[p][e][d]);
+              }
+          }
+        }
+  }
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+  for (int p = 0; p < NPT; ++p) {
+    const int kl = kl0 + tzb + p;
+    if (active && kl < g.nzl) {
+      double acc[NDOF];
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) acc[d] = 0.0;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
+        const double se = ss[tzb + p + oz][ty + oy][tx + ox];
+#pragma unroll
+        for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, t[p][e][d], acc[d]);
+      }
+      const long long r0 = (((long long)kl * g.NY + j) * g.NX + i) * NDOF;
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) {
+        const long long r = r0 + d;
+        const bool mr = mask && __ldg(mask + r);
+        const double xr = __ldg(x + r);
+        const double ax = mr ? bcdiag * xr : acc[d];
+        double out;
+        if (MODE == EMODE_SPMV) out = ax;
+        else if (MODE == EMODE_RESID) out = __ldg(b + r) - ax;
+        else out = xr + w * ((__ldg(b + r) - ax) / __ldg(diag + r));
+        y[r] = out;
+        if (partials) {
+          const double dv = dotv ? __ldg(dotv + r) : 0.0;
+          d0 = fma(out, xr, d0);
+          d1 = fma(xr, dv, d1);
+          d2 = fma(out, dv, d2);
+        }
+      }
+    }
+  }
+  if (partials) {
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if ((tid & 31) == 0) wred[0][tid >> 5] = d0, wred[1][tid >> 5] = d1, wred[2][tid >> 5] = d2;
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int v = 0; v < NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
+      const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      partials[3 * bid] = s0;
+      partials[3 * bid + 1] = s1;
+      partials[3 * bid + 2] = s2;
+    }
+  }
+}
+
 template <bool DIM3>
 static dim3 elem_grid(const Geo& g) {
   constexpr int BX = 32, BY = DIM3 ? 4 : 8, BZ = DIM3 ? 2 : 1;
   return dim3((g.NX + BX - 1) / BX, (g.NY + BY - 1) / BY, (g.nzl + BZ - 1) / BZ);
 }
 
+// ---- variant selection (3-D, ndof 1 or 3): 0 = one node per thread (elem_kernel); two nodes per thread with
+//      1 = 128-thread CTAs, 3 per SM (no register cap), 2 = 256-thread CTAs on a 32x4x4 brick, 2 per SM,
+//      3 = 128-thread CTAs, 4 per SM.  Chosen per process by pmb_elem_set_variant() / PMB_ELEM_VARIANT
+//      or measured by pmb_elem_autotune(); all variants produce bit-identical y.
+enum { PMB_ELEM_VARIANTS = 4 };
+static int g_elem_variant = -1;
+static int elem_variant() {
+  if (g_elem_variant < 0) {
+    const char* e = getenv("PMB_ELEM_VARIANT");
+    g_elem_variant = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+  }
+  return g_elem_variant;
+}
+extern "C" int pmb_elem_set_variant(int v) {
+  PMB_REQUIRE(v >= 0 && v < PMB_ELEM_VARIANTS, "pmb_elem_set_variant: variant %d not in 0..%d", v, PMB_ELEM_VARIANTS - 1);
+  g_elem_variant = v;
+  return 0;
+}
+extern "C" int pmb_elem_get_variant(void) { return elem_variant(); }
+
+template <int BY, int BZ>
+static dim3 elem_grid_v2(const Geo& g) {
+  return dim3((g.NX + 31) / 32, (g.NY + BY - 1) / BY, (g.nzl + BZ - 1) / BZ);
+}
+
+static dim3 elem_grid_any(const Geo& g, int variant) {
+  if (!g.dim3) return elem_grid<false>(g);
+  switch (variant) {
+    case 1: case 3: return elem_grid_v2<4, 2>(g);
+    case 2: return elem_grid_v2<4, 4>(g);
+  }
+  return elem_grid<true>(g);
+}
+
 extern "C" long long pmb_elem_ws_doubles(const pmb_grid* p) {
   if (validate_grid(p, "pmb_elem_ws_doubles")) return -1;
   Geo g = make_geo(p);
-  dim3 gr = g.dim3 ? elem_grid<true>(g) : elem_grid<false>(g);
-  return 3LL * gr.x * gr.y * gr.z;
+  long long m = 0;  // large enough for every variant, so the choice may change after workspaces were sized
+  for (int v = 0; v < PMB_ELEM_VARIANTS; ++v) {
+    dim3 gr = elem_grid_any(g, v);
+    const long long c = 3LL * gr.x * gr.y * gr.z;
+    m = c > m ? c : m;
+  }
+  return m;
 }
 
 template <int NDOF, bool DIM3, int MODE>
@@ -212,8 +426,21 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
                        double* dot_out, double* ws, cudaStream_t st) {
   KeParam<NDOF, DIM3> ke;
   memcpy(ke.v, Ke_host, sizeof(ke.v));
-  dim3 grid = elem_grid<DIM3>(g);
-  elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, dot_out ? ws : nullptr);
+  const int variant = (DIM3 && NDOF != 2) ? elem_variant() : 0;
+  dim3 grid = elem_grid_any(g, variant);
+  double* part = dot_out ? ws : nullptr;
+  if constexpr (DIM3 && NDOF != 2) {
+    if (variant == 1)
+      elem_kernel_v2<NDOF, MODE, 4, 1, 2, 3><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+    else if (variant == 2)
+      elem_kernel_v2<NDOF, MODE, 4, 2, 2, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+    else if (variant == 3)
+      elem_kernel_v2<NDOF, MODE, 4, 1, 2, 4><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+    else
+      elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+  } else {
+    elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+  }
   PMB_CHECK_LAUNCH("pmb_elem_spmv");
   if (dot_out) {
     reduce_triples_kernel<<<1, 1024, 0, st>>>(ws, (long long)grid.x * grid.y * grid.z, dot_out);
@@ -259,4 +486,38 @@ extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const double* Ke_host,
     }
   }
   return 1;
+}
+
+// Time every variant of the 3-D matrix-free kernel on the caller's buffers (Jacobi mode, y is scratch) and keep the
+// fastest for this process.  ms_out[4] receives the average launch time of each variant.  Not capturable.
+extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const double* s, const unsigned char* bcmask,
+                                 double bcdiagval, const double* x, const double* b, const double* diag, double* y,
+                                 double* ms_out, void* stream) {
+  if (validate_grid(p, "pmb_elem_autotune")) return 1;
+  PMB_REQUIRE(p->nz > 0, "pmb_elem_autotune: 3-D grids only");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return pmb_set_error("pmb_elem_autotune: cudaEventCreate failed");
+  const int saved = elem_variant();
+  int best = saved, rc = 0;
+  float best_ms = 1e30f;
+  for (int v = 0; v < PMB_ELEM_VARIANTS && !rc; ++v) {
+    g_elem_variant = v;
+    const int reps = 6;
+    for (int r = 0; r < 2 + reps && !rc; ++r) {
+      if (r == 2) cudaEventRecord(e0, st);
+      rc = pmb_elem_spmv(p, EMODE_JACOBI, Ke_host, s, bcmask, bcdiagval, x, b, diag, 0.5, y, nullptr, nullptr, nullptr, stream);
+    }
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = pmb_set_error("pmb_elem_autotune: %s", cudaGetErrorString(cudaGetLastError()));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= reps;
+    if (ms_out) ms_out[v] = ms;
+    if (!rc && ms < best_ms) best_ms = ms, best = v;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  g_elem_variant = rc ? saved : best;
+  return rc;
 }

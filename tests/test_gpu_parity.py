@@ -451,6 +451,68 @@ def test_matrix_free_operator_equals_assembled(pmb, shape, ndof):
         np.testing.assert_allclose(out2.cpu().numpy(), out.cpu().numpy(), rtol=0, atol=2e-13 * max(scale, np.abs(ref).max()))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3)])
+def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
+    """Every register / brick layout of the 3-D matrix-free kernel (pmb_elem_set_variant 1..3: two nodes per thread)
+    must reproduce variant 0 bit for bit in y (same products, same order per node) for all modes, on the whole grid and
+    on sub-slabs with odd plane counts; the fused dot products agree to rounding.  The autotune entry point runs, returns
+    one time per variant and leaves a valid selection."""
+    import ctypes as C
+
+    from pymoto_b200 import _lib, device as dv
+    from pymoto_b200.matrix import make_grid
+
+    rng = np.random.default_rng(5)
+    gr = Grid(*shape)
+    dom = pmb.VoxelDomain(*shape)
+    Ke = rng.standard_normal((8 * ndof,) * 2)
+    Ke = Ke + Ke.T + 8 * np.eye(Ke.shape[0])
+    bc = np.unique(rng.integers(0, gr.nnodes * ndof, 17))
+    K = pmb.AssembleGeneral(dom, Ke, bc=bc)(rng.random(gr.nel))
+    n = K.shape[0]
+    vd, bd = dv.to_device(rng.standard_normal(n)), dv.to_device(rng.standard_normal(n))
+    D = K.diagonal_device()
+    saved = _lib.query("pmb_elem_get_variant")
+    try:
+        ref = {}
+        for variant in range(4):
+            _lib.call("pmb_elem_set_variant", variant)
+            assert _lib.query("pmb_elem_get_variant") == variant
+            for mode in (_lib.SPMV, _lib.RESIDUAL, _lib.JACOBI):
+                out, d3 = dv.zeros(n), dv.empty(3)
+                K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
+                got = (out.cpu().numpy(), d3.cpu().numpy())
+                if variant == 0:
+                    ref[mode] = got
+                else:
+                    assert np.array_equal(got[0], ref[mode][0]), (variant, mode)
+                    np.testing.assert_allclose(got[1], ref[mode][1], rtol=1e-11, atol=1e-9)
+            # a sub-slab [k0, k0 + 3) of the same operator: pointers move with the slab, halo planes are read around it
+            g, k0, npl = K.grid, 1, 3
+            sg = make_grid(g.nx, g.ny, g.nz, g.ndof, k0, npl)
+            plane, lay = K.plane, g.nx * g.ny
+            gen = K.generator
+            out = dv.zeros(n)
+            _lib.call("pmb_elem_spmv", sg, _lib.JACOBI, gen["ke"].ctypes.data, gen["s"].data_ptr() + 8 * k0 * lay,
+                      gen["mask"].data_ptr() + k0 * plane, float(gen["bcdiag"]), vd.data_ptr() + 8 * k0 * plane,
+                      bd.data_ptr() + 8 * k0 * plane, D.data_ptr() + 8 * k0 * plane, 0.5, out.data_ptr() + 8 * k0 * plane,
+                      None, None, None, dv.stream())
+            got = out.cpu().numpy()
+            want = np.zeros(n)
+            want[k0 * plane:(k0 + npl) * plane] = ref[_lib.JACOBI][0][k0 * plane:(k0 + npl) * plane]
+            assert np.array_equal(got, want), ("slab", variant)
+        ms = (C.c_double * 4)()
+        scratch = dv.zeros(n)
+        _lib.call("pmb_elem_autotune", K.grid, gen["ke"].ctypes.data, gen["s"].data_ptr(), gen["mask"].data_ptr(),
+                  float(gen["bcdiag"]), vd.data_ptr(), bd.data_ptr(), D.data_ptr(), scratch.data_ptr(), C.addressof(ms), dv.stream())
+        assert all(0.0 < t < 1e3 for t in ms)
+        assert 0 <= _lib.query("pmb_elem_get_variant") < 4
+        assert np.array_equal(scratch.cpu().numpy(), ref[_lib.JACOBI][0])
+    finally:
+        _lib.call("pmb_elem_set_variant", saved)
+
+
 # ------------------------------------------------------------------------------------------------ FilterConv (next row f1)
 FILTERCONV_KW = {
     "sym3d": dict(radius=2.0),
