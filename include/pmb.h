@@ -22,6 +22,12 @@
  *                        pymoto/modules/filter.py:182-220     (FilterConv: index-mapped padding, scipy.signal convolve/correlate)
  *   pmb_filter_apply / pmb_vec_div
  *                        pymoto/modules/filter.py:266-270     (csc_matvec of H, division by Hs)
+ *   pmb_oc_candidate     pymoto/common/optimizers.py:425-435  (OC bisection candidate)
+ *   pmb_mma_asymptotes / pmb_mma_setup
+ *                        pymoto/common/mma.py:129-140,178-217 (asymptote offsets; low/upp/alfa/beta/P/Q, rhs sums)
+ *   pmb_mma_residual / pmb_mma_newton_sums / pmb_mma_newton_dir / pmb_mma_linesearch
+ *                        pymoto/common/mma.py:313-336,349-392,401-423,428-462 (n-sized parts of subsolv)
+ *   pmb_pack_f32         pymoto/common/domain.py:541-548,579-583 (Float32 VTI payload, 2 -> 3 component padding)
  *
  * Conventions
  *   - all functions return 0 on success, non-zero on error; pmb_last_error() gives the (thread-local) message.
@@ -191,6 +197,45 @@ int pmb_oc_candidate(long long n, const double* x, const double* dg, double move
 /* SIMP glue kept on device for the resident path: s = xmin + (1-xmin) y^p ; dy = ds * p (1-xmin) y^(p-1) */
 int pmb_simp(long long n, double xmin, int p, const double* y, double* s, void* stream);
 int pmb_simp_bwd(long long n, double xmin, int p, const double* y, const double* ds, double* dy, void* stream);
+
+/* ---- MMA design update (pymoto/common/mma.py), n-sized parts; the m-sized unknowns stay with the caller on the host.
+ * m = number of general constraints (1..PMB_MMA_MAXM; an unconstrained problem passes one dummy row of zeros like the
+ * reference does).  P, Q: (m+1) x n row-major.  All `out` arrays are DEVICE memory, sums first then maxima; every pass is a
+ * deterministic two-stage reduction over ws (pmb_mma_ws_doubles() doubles, zero-initialised once by the caller). */
+#define PMB_MMA_MAXM 3
+typedef struct {
+  double s;        /* value for every variable ...                  */
+  const double* v; /* ... unless v != NULL: per-variable device array */
+} pmb_bound;
+typedef struct {
+  double *x, *xsi, *eta;           /* subproblem iterate: primal x and the multipliers of alfa <= x <= beta */
+  double *xo, *xsio, *etao;        /* line-search base point (written by pmb_mma_newton_dir)                */
+  double *dx, *dxsi, *deta;        /* Newton direction                                                       */
+  double *low, *upp, *alfa, *beta; /* asymptotes, move-limited bounds                                        */
+  double *P, *Q;                   /* (m+1) x n                                                              */
+} pmb_mma_vecs;
+long long pmb_mma_ws_doubles(void);
+/* offset *= asyincr / asydecr by the sign of (x-xold1)(xold1-xold2), clipped to [1/asybound^2, asybound] (mma.py:129-140) */
+int pmb_mma_asymptotes(long long n, const double* x, const double* xold1, const double* xold2, double asyincr, double asydecr,
+                       double asybound, double* offset, void* stream);
+/* mmasub set-up (mma.py:178-217) + subsolv start point (:288-293).  dg: HOST array of m+1 device row pointers; rho: HOST
+ * array of m+1 values; version 1987 | 2007.  out[i] = sum_j (P_ij + Q_ij) / shift_j, i = 0..m (rhs = out - g on the host). */
+int pmb_mma_setup(long long n, int m, const double* xval, const double* const* dg, const double* offset, pmb_bound xmin,
+                  pmb_bound xmax, pmb_bound move, double albefa, const double* rho, int version, const pmb_mma_vecs* v,
+                  double* out, double* ws, void* stream);
+/* lam, dlam: HOST arrays of m values.  residual / linesearch: out = [sum of squared x-, xsi-, eta-residuals, gvec[m], max
+ * squared residual]; newton_sums: out = [gvec[m], GG (delx/diagx) [m], (GG/diagx) GG^T [m*m]]; newton_dir stores dx, dxsi,
+ * deta, xo, xsio, etao and out = [0, max(-dxsi/xsi), max(-deta/eta), max(-dx/(x-alfa)), max(dx/(beta-x))]; linesearch sets
+ * (x, xsi, eta) = base + steg * direction before evaluating the residual. */
+int pmb_mma_residual(long long n, int m, const pmb_mma_vecs* v, const double* lam, double epsi, double* out, double* ws, void* stream);
+int pmb_mma_newton_sums(long long n, int m, const pmb_mma_vecs* v, const double* lam, double epsi, double* out, double* ws, void* stream);
+int pmb_mma_newton_dir(long long n, int m, const pmb_mma_vecs* v, const double* lam, const double* dlam, double epsi, double* out,
+                       double* ws, void* stream);
+int pmb_mma_linesearch(long long n, int m, const pmb_mma_vecs* v, const double* lam, double steg, double epsi, double* out,
+                       double* ws, void* stream);
+
+/* VTI writer payload: out[i*ncomp_out + c] = (float) in[i*ncomp_in + c], zero for c >= ncomp_in (round to nearest even) */
+int pmb_pack_f32(long long nitems, int ncomp_in, int ncomp_out, const double* in, float* out, void* stream);
 
 #ifdef __cplusplus
 }

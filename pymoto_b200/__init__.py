@@ -17,12 +17,13 @@ from .dyad import DeviceDyad
 from .assembly import AssembleGeneral, AssembleStiffness, AssemblePoisson
 from .filter import DensityFilter, Filter, FilterConv
 from .linalg import LinSolve
-from .glue import SIMP, Compliance
+from .glue import SIMP, Compliance, Sum, Scaling
 from . import solvers
-from .optimizers import OC, minimize_oc
+from .optimizers import OC, minimize_oc, MMA, minimize_mma
+from .io import WriteToVTI, write_to_vti
 from . import slab
 from ._lib import PmbError
 
 __all__ = ["Signal", "Module", "Network", "VoxelDomain", "DomainDefinition", "DeviceCSR", "DeviceDyad",
-           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "FilterConv", "LinSolve", "SIMP", "Compliance", "solvers", "slab", "OC", "minimize_oc",
+           "AssembleGeneral", "AssembleStiffness", "AssemblePoisson", "DensityFilter", "Filter", "FilterConv", "LinSolve", "SIMP", "Compliance", "Sum", "Scaling", "solvers", "slab", "OC", "minimize_oc", "MMA", "minimize_mma", "WriteToVTI", "write_to_vti",
            "PmbError", "HAVE_PYMOTO"]

@@ -33,6 +33,21 @@ def coef(c=1.0, num=None, den=None, sqrt_den=False):
     return Coef(float(c), num, den, 1 if sqrt_den else 0)
 
 
+class Bound(C.Structure):
+    """Mirror of ``pmb_bound``: one value for every variable, or a per-variable device array."""
+
+    _fields_ = [("s", C.c_double), ("v", C.c_void_p)]
+
+
+class MmaVecs(C.Structure):
+    """Mirror of ``pmb_mma_vecs`` (device pointers of the n-sized MMA subproblem state)."""
+
+    NAMES = ("x", "xsi", "eta", "xo", "xsio", "etao", "dx", "dxsi", "deta", "low", "upp", "alfa", "beta", "P", "Q")
+    _fields_ = [(nm, C.c_void_p) for nm in NAMES]
+
+
+MMA_MAXM = 3  # PMB_MMA_MAXM
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _D = C.c_double
@@ -81,6 +96,15 @@ SIGNATURES = {
     "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_halo_copy2": (_I, [_LL, _P, _P, _P, _P, _P]),
     "pmb_oc_candidate": (_I, [_LL, _P, _P, _D, _D, _D, _D, _P, _P, _P, _P]),
+    "pmb_mma_ws_doubles": (_LL, []),
+    "pmb_mma_asymptotes": (_I, [_LL, _P, _P, _P, _D, _D, _D, _P, _P]),
+    "pmb_mma_setup": (_I, [_LL, _I, _P, C.POINTER(C.c_void_p), _P, Bound, Bound, Bound, _D, C.POINTER(C.c_double), _I,
+                           C.POINTER(MmaVecs), _P, _P, _P]),
+    "pmb_mma_residual": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _P, _P, _P]),
+    "pmb_mma_newton_sums": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _P, _P, _P]),
+    "pmb_mma_newton_dir": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _P, _P, _P]),
+    "pmb_mma_linesearch": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _D, _P, _P, _P]),
+    "pmb_pack_f32": (_I, [_LL, _I, _I, _P, _P, _P]),
     "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
     "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),
 }

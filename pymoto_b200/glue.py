@@ -55,3 +55,68 @@ class Compliance(Module):
         if self._host:
             return du.cpu().numpy(), df.cpu().numpy()
         return du, df
+
+
+class Sum(Module):
+    """v = sum_i x_i (``EinSum('i->')``, the volume of a density field): deterministic device reduction."""
+
+    _ones = {}
+
+    def __call__(self, x):
+        xd = dv.to_device(x).reshape(-1)
+        self._n, self._host = xd.numel(), not dv.is_device(x)
+        key = (xd.device.index, self._n)
+        if key not in Sum._ones:
+            import torch
+
+            Sum._ones.clear()  # one cached vector of ones (the current problem size)
+            Sum._ones[key] = torch.ones(self._n, dtype=torch.float64, device=xd.device)
+        v = dv.dots([(xd, Sum._ones[key])])[0]
+        return float(v.item()) if self._host else v
+
+    def _sensitivity(self, dvol):
+        import torch
+
+        val = float(dvol.item()) if dv.is_device(dvol) else float(dvol)
+        d = torch.full((self._n,), val, dtype=torch.float64, device=dv.require_cuda())
+        return d.cpu().numpy() if self._host else d
+
+
+class Scaling(Module):
+    """Objective / constraint scaling of a scalar response (pymoto/modules/scaling.py:8-125): objective
+    ``y = x * scaling / |x_0|``; constraint ``(x - maxval)/|maxval| * scaling`` or ``(minval - x)/|minval| * scaling`` (or the
+    smoothed two-sided form).  Scalar arithmetic only -- works on host floats and on 0-d CUDA tensors alike."""
+
+    def __init__(self, scaling: float = 100.0, minval: float = None, maxval: float = None, minmax_smooth: float = 1e-2):
+        self.minval, self.maxval, self.scaling, self.minmax_smooth = minval, maxval, scaling, minmax_smooth
+        self.sf = None
+        self.reset_scaling()
+
+    def __call__(self, x):
+        self._x = x
+        if self.sf is None:
+            self.sf = self.scaling / abs(float(x))
+        if self.minval is not None and self.maxval is not None:
+            midp, diff = (self.minval + self.maxval) / 2, (self.maxval - self.minval) / 2
+            g = ((x - midp) ** 2 + self.minmax_smooth * diff ** 2) ** 0.5 - ((1 + self.minmax_smooth) * diff ** 2) ** 0.5
+        elif self.minval is not None:
+            g = (self.minval - x) / (1 if self.minval == 0 else abs(self.minval))
+        elif self.maxval is not None:
+            g = (x - self.maxval) / (1 if self.maxval == 0 else abs(self.maxval))
+        else:
+            g = x
+        return g * self.sf
+
+    def _sensitivity(self, dy):
+        dg = dy * self.sf
+        if self.minval is not None and self.maxval is not None:
+            midp, diff = (self.minval + self.maxval) / 2, (self.maxval - self.minval) / 2
+            return dg * (self._x - midp) / ((self._x - midp) ** 2 + self.minmax_smooth * diff ** 2) ** 0.5
+        if self.minval is not None:
+            return -dg / (1 if self.minval == 0 else abs(self.minval))
+        if self.maxval is not None:
+            return dg / (1 if self.maxval == 0 else abs(self.maxval))
+        return dg
+
+    def reset_scaling(self):
+        self.sf = self.scaling if (self.minval is not None or self.maxval is not None) else None

@@ -2,6 +2,8 @@
 unmodified reference.  Bit-exact where the contract says so (CSR pattern, assembled values, filter, transfer
 operators); tolerances written next to each floating-point comparison (north star: values rtol 1e-12, relative
 residual <= 1e-8, compliance within 1e-6 relative)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -778,3 +780,133 @@ def test_linsolve_multiple_rhs_and_finite_difference(pmb):
         lsp = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=pmb.solvers.auto_multigrid(dom, min_size=2)[0], tol=1e-12))
         cp = lsp(asm(xp), P.f) @ P.f
         assert abs((cp - c0) / 1e-6 - dcdx[e]) <= 2e-4 * abs(dcdx[e]) + 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ MMA on the device (next row f3)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds"])
+def test_mma_device_update_vs_reference_golden(pmb, name):
+    """pmb_mma_* kernels + the host Newton driver against pym.MMA.step on seeded subproblems (m = 1, 2, 3 constraints,
+    unconstrained, MMA1987, vector bounds): asymptotes to rounding, new design within 2e-9 absolute."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_opt_inputs import subsolv_inputs
+    from pymoto_b200 import device as dv
+    from pymoto_b200.optimizers import MmaDeviceOps, mma_design_update
+
+    g = load("mma_subsolv")
+    p = subsolv_inputs(name)
+    n, m = p["n"], max(1, p["nresp"] - 1)
+    ops = MmaDeviceOps(n, m)
+    offset = dv.to_device(np.full(n, 0.5))
+    bnd = {k: (dv.to_device(p[k]) if isinstance(p[k], np.ndarray) else p[k]) for k in ("xmin", "xmax", "move")}
+    opt = dict(albefa=0.1, asyincr=1.2, asydecr=0.7, asybound=10.0, a0=1.0, epsimin=1e-10, rho=1e-5,
+               version=1987 if "1987" in p["version"] else 2007, a=np.zeros(m), c=np.full(m, 1e3), d=np.ones(m))
+    lam, its = mma_design_update(ops, dv.to_device(p["x"]), p["g"].copy(), [dv.to_device(r) for r in p["dg"]], offset,
+                                 dv.to_device(p["xold1"]), dv.to_device(p["xold2"]), bnd["xmin"], bnd["xmax"], bnd["move"], opt)
+    np.testing.assert_allclose(offset.cpu().numpy(), g[name + "_offset"], rtol=1e-15)
+    np.testing.assert_allclose(ops.t["low"].cpu().numpy(), g[name + "_low"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(ops.t["upp"].cpu().numpy(), g[name + "_upp"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(ops.x.cpu().numpy(), g[name + "_xnew"], rtol=0, atol=2e-9)
+    assert 5 < its < 200 and np.all(lam > 0)
+    # the reductions are deterministic: a second solve of the same subproblem reproduces the design bit for bit
+    first = ops.x.clone()
+    offset2 = dv.to_device(np.full(n, 0.5))
+    mma_design_update(ops, dv.to_device(p["x"]), p["g"].copy(), [dv.to_device(r) for r in p["dg"]], offset2,
+                      dv.to_device(p["xold1"]), dv.to_device(p["xold2"]), bnd["xmin"], bnd["xmax"], bnd["move"], opt)
+    assert bool((ops.x == first).all())
+
+
+def _mma_chain(pmb, dom, bc, f, host):
+    from pymoto_b200 import device as dv
+
+    fd = f if host else dv.to_device(f)
+    x0 = np.full(dom.nel, 0.5)
+    sx = pmb.Signal("x", state=x0 if host else dv.to_device(x0))
+    with pmb.Network() as fn:
+        sy = pmb.DensityFilter(dom, radius=2.0)(sx)
+        ss = pmb.SIMP(1e-9, 3)(sy)
+        sK = pmb.AssembleStiffness(dom, bc=bc)(ss)
+        mgs = pmb.solvers.auto_multigrid(dom)
+        su = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=mgs[0], tol=1e-10))(sK, fd)
+        sc = pmb.Compliance()(su, fd)
+        sg0 = pmb.Scaling(scaling=100.0)(sc)
+        sv = pmb.Sum()(sy)
+        sg1 = pmb.Scaling(scaling=10.0, maxval=0.5 * dom.nel)(sv)
+    sg0.tag, sg1.tag = "objective", "volume constraint"
+    return sx, [sg0, sg1], fn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,host", [("mma_mbb60x30", False), ("mma_hex16x8x8", False), ("mma_hex16x8x8", True)])
+def test_mma_design_loop_vs_reference_history(pmb, case, host):
+    """pymoto_b200.MMA driving the device chain (filter, SIMP, assembly, CG+GMG, compliance, scaled objective and volume
+    constraint) against the reference's own MMA2007 history of the same problem (direct solver), design by design; both
+    with CUDA-tensor Signals (resident loop) and with numpy Signals (reference glue compatible)."""
+    g = load(case)
+    if case == "mma_mbb60x30":
+        nx, ny = 60, 30
+        dom = pmb.VoxelDomain(nx, ny)
+        nodes = dom.nodes
+        bc = np.concatenate([2 * nodes[0, :].flatten(), 2 * nodes[nx, 0].flatten() + 1])
+        f = np.zeros(dom.nnodes * 2)
+        f[2 * nodes[0, ny].flatten() + 1] = -1.0
+    else:
+        nx, ny, nz = 16, 8, 8
+        dom = pmb.VoxelDomain(nx, ny, nz)
+        ndof, bc, f = cantilever(Grid(nx, ny, nz))
+    sx, resp, fn = _mma_chain(pmb, dom, bc, f, host)
+    mma = pmb.MMA(sx, resp, fn, verbosity=0)
+    ghist, x, xs = [], None, []
+    for it in range(len(g["ghist"])):
+        xnew, gv, dg = mma.step(x)
+        ghist.append(np.array(gv, dtype=float))
+        x = xnew
+        xs.append(x.cpu().numpy())
+        assert mma.newton_iterations > 0
+    np.testing.assert_allclose(np.array(ghist), g["ghist"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(xs[0], g["x1"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(xs[1], g["x2"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(xs[-1], g["xlast"], rtol=0, atol=1e-4)
+    # asymptote offsets follow sign decisions on (x - xold1)(xold1 - xold2): allow a few flips where a variable barely moves
+    assert np.mean(np.abs(mma.offset.cpu().numpy() / g["offset_last"] - 1.0) > 1e-9) < 0.01
+    assert isinstance(sx.state, np.ndarray) == host
+    # minimize_mma runs to a stopping criterion
+    sx2, resp2, fn2 = _mma_chain(pmb, dom, bc, f, host)
+    m2 = pmb.minimize_mma(sx2, resp2, function=fn2, maxit=2, verbosity=0)
+    assert m2.iter <= 2
+    with pytest.raises(NotImplementedError):
+        pmb.MMA(sx2, resp2, fn2, mmaversion="GCMMA")
+
+
+# ------------------------------------------------------------------------------------------------ VTI output of device fields (f4)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["2d", "3d", "block"])
+def test_write_to_vti_from_device_tensors(pmb, name, tmp_path):
+    """Fields resident on the GPU are packed to Float32 by pmb_pack_f32 and written byte-for-byte like the reference's
+    VoxelDomain.write_to_vti; mixing numpy and CUDA inputs is allowed; the WriteToVTI module numbers its files."""
+    import sys
+
+    import torch
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_opt_inputs import vti_inputs
+
+    shape, vecs, scale = vti_inputs(name)
+    dom = pmb.VoxelDomain(*shape)
+    want = load("vti")[name]
+    dev = {k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if not np.iscomplexobj(v) else v) for k, v in vecs.items()}
+    fn = str(tmp_path / "dev.vti")
+    pmb.write_to_vti(dom, dev, fn, scale=scale)
+    got = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+    assert got.size == want.size and np.array_equal(got, want)
+    if name == "3d":
+        w = pmb.WriteToVTI(dom, str(tmp_path / "out" / "dat.vti"), scale=scale, interval=2)
+        sigs = [pmb.Signal(k, state=v) for k, v in dev.items()]
+        w(*sigs)
+        w.response()  # iteration 1: skipped by the interval
+        w.response()
+        files = sorted(os.listdir(tmp_path / "out"))
+        assert files == ["dat.0000.vti", "dat.0002.vti"], files
+        assert np.array_equal(np.frombuffer(open(tmp_path / "out" / files[1], "rb").read(), dtype=np.uint8), want)
