@@ -498,7 +498,7 @@ def run_b200(args, full):
         flops = 2.0 * 8 * (8 * ndof_ * ndof_ + ndof_) * (n / ndof_)  # 8 elements x (8 nodes x ndof^2 + ndof) FMA per node
         matrix_free = {"kernel": f"elem_kernel<{A.grid.ndof},3D,JACOBI> (finest level from element densities)", "kernel_ms": mf_ms,
                        "bound": "fp64 pipe", "fp64_tflops": flops / (mf_ms * 1e-3) / 1e12, "dram_bytes_algorithmic": 40 * n + 8 * nel,
-                       "variant": _lib.query("pmb_elem_get_variant"), "variant_ms_autotune": DeviceCSR.elem_timings_ms,
+                       "variant": _lib.query("pmb_elem_get_variant", ndof_), "variant_ms_autotune": DeviceCSR.elem_timings_ms.get(ndof_),
                        "launches_per_step": fine_mf / K, "share_of_step": (fine_mf / K) * mf_ms / step_avg_ms,
                        "speedup_vs_streaming_assembled_values": kern_ms / mf_ms,
                        "assembled_layout_time_at_100pct_hbm_peak_ms": alg_bytes / (peak * 1e9) * 1e3,

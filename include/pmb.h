@@ -110,12 +110,14 @@ int pmb_elem_spmv(const pmb_grid* g, int mode, const double* Ke_host, const doub
                   double bcdiagval, const double* x, const double* b, const double* diag, double w, double* y,
                   const double* dotv, double* dot_out, double* ws, void* stream);
 long long pmb_elem_ws_doubles(const pmb_grid* g);
-/* The 3-D kernel behind pmb_elem_spmv exists in 4 register / brick layouts (0 = one node per thread, 1..3 = two nodes
- * per thread stacked along z; y is bit-identical for all).  set/get pin or read the layout used by this process
- * (initially PMB_ELEM_VARIANT or 0); pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's
- * operands, stores the launch times in ms_out[4] and keeps the fastest.  Not capturable into a CUDA graph. */
+/* The 3-D kernel behind pmb_elem_spmv exists in pmb_elem_num_variants() layouts (0 = one node per thread on a 32x4x2
+ * brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered planes; y is bit-identical for all).  set pins the layout for this process, get reads the one used for `ndof` dofs per node (initially PMB_ELEM_VARIANT or
+ * 0);
+ * pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's operands, stores the launch times in
+ * ms_out[pmb_elem_num_variants()] and keeps the fastest for that ndof.  Not capturable into a CUDA graph. */
 int pmb_elem_set_variant(int variant);
-int pmb_elem_get_variant(void);
+int pmb_elem_get_variant(int ndof);
+int pmb_elem_num_variants(void);
 int pmb_elem_autotune(const pmb_grid* g, const double* Ke_host, const double* s, const unsigned char* bcmask,
                       double bcdiagval, const double* x, const double* b, const double* diag, double* y,
                       double* ms_out, void* stream);

@@ -69,7 +69,8 @@ SIGNATURES = {
     "pmb_elem_spmv": (_I, [_G, _I, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "pmb_elem_ws_doubles": (_LL, [_G]),
     "pmb_elem_set_variant": (_I, [_I]),
-    "pmb_elem_get_variant": (_I, []),
+    "pmb_elem_get_variant": (_I, [_I]),
+    "pmb_elem_num_variants": (_I, []),
     "pmb_elem_autotune": (_I, [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P]),
     "pmb_ws_doubles": (_LL, []),
     "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
@@ -123,7 +124,7 @@ def _kernels_launched(name, args):
     if name == "pmb_elem_spmv":
         return 2 if args[12] is not None else 1
     if name == "pmb_elem_autotune":
-        return 4 * 8  # every variant: 2 warm-up + 6 timed launches
+        return 8 * load().pmb_elem_num_variants()  # every variant: 2 warm-up + 6 timed launches
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":

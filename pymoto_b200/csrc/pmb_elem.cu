@@ -195,147 +195,200 @@ __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Variant 2 (3-D only): NPT nodes per thread, stacked along z.  The kernel above issues ~3.1 instructions per DFMA
-// (one LDCU.128 of two Ke constants per two DFMAs, 81 LDS per node, staging and epilogue per node), so the issue
-// slots -- not the FP64 pipe (one warp DFMA per 2 cycles per SM sub-partition) -- bound it.  Stacking NPT nodes per
-// thread lets every uniform-register load of a Ke constant feed NPT DFMAs and amortises the staging of the brick
-// apron over a larger brick.  Epilogue operands are loaded after the FMA phase to keep the
-// 24 NPT accumulators in registers.  Same arithmetic per node in the same order, so both variants give identical y
-// (the fused dot-product partials are grouped differently).
+// z-marching layout (3-D).  Source-level stall sampling of elem_kernel (profiles/ncu_elem_variants_r1.txt) puts ~60 % of
+// the warp samples and 43 % of the executed instructions in the brick staging prologue (index arithmetic, predicates,
+// global-load latency before the barrier), not in the FMA phase.  Here a CTA owns a 32 x BY column of nodes and marches
+// over ZM_L consecutive node planes: the masked x planes live in a 4-slot shared-memory ring (3 in use, 1 being filled by
+// cp.async), the element densities in a second ring; staging offsets and validity are computed once per CTA and the
+// copies of the NEXT plane are in flight during the FMA phase.  Per element the same (dk, dj, di) FMA order as
+// elem_kernel, so y is bit-identical.  Measured (B200, 256x128x128): ndof = 3 0.37 ms vs 0.35 ms for the brick kernel
+// (the FMA phase dominates there and the brick kernel's higher occupancy wins); ndof = 1 0.52 ms vs 0.70 ms.
 // ---------------------------------------------------------------------------------------------------------
-template <int NDOF, int MODE, int BY, int BZT, int NPT, int MINB>
-__global__ void __launch_bounds__(32 * BY * BZT, MINB)
-    elem_kernel_v2(Geo g, const __grid_constant__ KeParam<NDOF, true> ke, const double* __restrict__ s,
+constexpr int ZM_BX = 32, ZM_L = 8;
+
+// 8-byte asynchronous global -> shared copy (LDGSTS); `valid == false` zero-fills the destination without reading src
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int NDOF, int MODE, int BY, int MINB>
+__global__ void __launch_bounds__(32 * BY, MINB)
+    elem_kernel_zm(Geo g, const __grid_constant__ KeParam<NDOF, true> ke, const double* __restrict__ s,
                    const unsigned char* __restrict__ mask, double bcdiag, const double* __restrict__ x,
                    const double* __restrict__ b, const double* __restrict__ diag, double w, double* __restrict__ y,
                    const double* __restrict__ dotv, double* __restrict__ partials) {
-  constexpr int NT = 32 * BY * BZT;
-  constexpr int BX = 32, BZ = BZT * NPT;
-  constexpr int TX = BX + 2, TY = BY + 2, TZ = BZ + 2;
-  constexpr int SZ = BZ + 1;
+  constexpr int BX = ZM_BX, NT = 32 * BY;
+  constexpr int TX = BX + 2, TY = BY + 2;
+  constexpr int ROWLEN = TX * NDOF, PLANE = TY * ROWLEN;   // doubles per staged x plane
+  constexpr int SLAY = (BY + 1) * (BX + 1);                // densities per staged element layer
+  constexpr int NQ = (PLANE + NT - 1) / NT, NQS = (SLAY + NT - 1) / NT;
   constexpr int LD = KeParam<NDOF, true>::LD;
-  constexpr int ROWLEN = TX * NDOF;
-  constexpr int RP = NT / 128;  // brick rows staged per pass (128 threads each)
-  static_assert(NT % 128 == 0 && ROWLEN <= 128, "staging layout");
-  __shared__ double su[TZ][TY][ROWLEN];
-  __shared__ double ss[SZ][BY + 1][BX + 1];
+  __shared__ double su[4][PLANE];
+  __shared__ double ss[4][SLAY];
   __shared__ double wred[3][NT / 32];
 
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, kl0 = blockIdx.z * BZ;
-  const long long safe = (((long long)kl0 * g.NY + j0) * g.NX + i0) * NDOF;  // first dof of the brick: always owned
-  {
-    constexpr int NROW = TZ * TY, NQ = (NROW + RP - 1) / RP;
-    const int col = tid & 127, sub = tid >> 7;
-    const int i = i0 - 1 + col / NDOF;
-    const bool colin = col < ROWLEN && i >= 0 && i < g.NX;
-    double xv[NQ];
-    unsigned char mk[NQ];
-    bool inb[NQ];
+  const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
+  const int kA = blockIdx.z * ZM_L;                                  // first owned local plane of this CTA
+  const int kB = min(kA + ZM_L, g.nzl);                              // one past its last
+  const long long xplane = (long long)g.NX * g.NY * NDOF;            // dofs per node plane
+  const long long slayer = (long long)g.nx * g.ny;                   // elements per layer
+
+  // ---- per-thread staging slots: offsets inside a plane / layer and in-grid flags, computed once
+  int xoff[NQ], soff[NQS];
+  bool xok[NQ], sok[NQS];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int row = RP * q + sub;
-      const int ty = row % TY, tz = row / TY;
-      const int j = j0 - 1 + ty, k = g.kz0 + kl0 - 1 + tz;
-      inb[q] = colin && row < NROW && j >= 0 && j < g.NY && k >= 0 && k < g.NZ && k <= g.kz0 + g.nzl;
-      const long long idx = inb[q] ? (((long long)(k - g.kz0) * g.NY + j) * g.NX + (i0 - 1)) * NDOF + col : safe;
-      xv[q] = __ldg(x + idx);
-      mk[q] = mask ? __ldg(mask + idx) : (unsigned char)0;
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int row = RP * q + sub;
-      if (col < ROWLEN && row < NROW) su[row / TY][row % TY][col] = (inb[q] && !mk[q]) ? xv[q] : 0.0;
-    }
+  for (int q = 0; q < NQ; ++q) {
+    const int p = tid + NT * q;
+    const int row = p / ROWLEN, col = p - row * ROWLEN;
+    const int i = i0 - 1 + col / NDOF, j = j0 - 1 + row;
+    xok[q] = p < PLANE && i >= 0 && i < g.NX && j >= 0 && j < g.NY;
+    xoff[q] = (j * g.NX + (i0 - 1)) * NDOF + col;
   }
-  {
-    constexpr int NS = SZ * (BY + 1) * (BX + 1), NQ = (NS + NT - 1) / NT;
-    double sv[NQ];
-    bool sin[NQ];
+#pragma unroll
+  for (int q = 0; q < NQS; ++q) {
+    const int p = tid + NT * q;
+    const int ty = p / (BX + 1), tx = p - ty * (BX + 1);
+    const int ei = i0 - 1 + tx, ej = j0 - 1 + ty;
+    sok[q] = p < SLAY && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny;
+    soff[q] = ej * g.nx + ei;
+  }
+  // plane kl (local, may be -1 or nzl = halo) exists and may be read
+  auto plane_ok = [&](int kl) {
+    const int k = g.kz0 + kl;
+    return k >= 0 && k < g.NZ && kl <= g.nzl;
+  };
+  auto layer_ok = [&](int el) {  // element layer el (local): layers above the last owned node plane are never needed
+    const int ek = g.kz0 + el;
+    return ek >= 0 && ek < g.nzE && el < g.nzl;
+  };
+  // Asynchronous staging: cp.async copies x / s straight into the ring slot (zero-fill outside the grid), so no register
+  // holds a staged value across the FMA phase; only the Dirichlet mask bytes of the slots travel in registers and are
+  // applied (slot zeroed) once the copies have landed.
+  auto issue_plane = [&](int kl, int slot, unsigned char (&mk)[NQ]) {
+    const bool pok = plane_ok(kl);
+    const double* xp = x + (long long)kl * xplane;
+    const unsigned char* mp = mask + (long long)kl * xplane;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int p = tid + NT * q;
-      const int tx = p % (BX + 1), ty = (p / (BX + 1)) % (BY + 1), tz = p / ((BX + 1) * (BY + 1));
-      const int ei = i0 - 1 + tx, ej = j0 - 1 + ty, ek = g.kz0 + kl0 - 1 + tz;
-      sin[q] = p < NS && ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE && ek < g.kz0 + g.nzl;
-      const long long sidx = sin[q] ? ((long long)(ek - g.kz0) * g.ny + ej) * g.nx + ei : 0;
-      sv[q] = __ldg(s + sidx);
+      const bool ok = pok && xok[q];
+      if (p < PLANE) cp_async8(&su[slot][p], ok ? xp + xoff[q] : x, ok);
+      mk[q] = (mask && ok) ? __ldg(mp + xoff[q]) : (unsigned char)0;
     }
+  };
+  auto mask_plane = [&](int slot, const unsigned char (&mk)[NQ]) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
+    for (int q = 0; q < NQ; ++q)
+      if (mk[q]) su[slot][tid + NT * q] = 0.0;
+  };
+  auto issue_layer = [&](int el, int slot) {
+    const bool lok = layer_ok(el);
+    const double* sp = s + (long long)el * slayer;
+#pragma unroll
+    for (int q = 0; q < NQS; ++q) {
       const int p = tid + NT * q;
-      if (p < NS) ss[p / ((BX + 1) * (BY + 1))][(p / (BX + 1)) % (BY + 1)][p % (BX + 1)] = sin[q] ? sv[q] : 0.0;
+      const bool ok = lok && sok[q];
+      if (p < SLAY) cp_async8(&ss[slot][p], ok ? sp + soff[q] : s, ok);
     }
+  };
+
+  // ---- prime the rings: planes kA-1, kA, kA+1 -> slots 0, 1, 2; layers kA-1, kA -> slots 0, 1 (all copies in flight at once)
+  {
+    unsigned char m0[NQ], m1[NQ], m2[NQ];
+    issue_plane(kA - 1, 0, m0);
+    issue_plane(kA, 1, m1);
+    issue_plane(kA + 1, 2, m2);
+    issue_layer(kA - 1, 0);
+    issue_layer(kA, 1);
+    cp_async_wait_all();
+    mask_plane(0, m0);
+    mask_plane(1, m1);
+    mask_plane(2, m2);
   }
-  const int tx = tid % BX, ty = (tid / BX) % BY, tzb = (tid / (BX * BY)) * NPT;
-  const int i = i0 + tx, j = j0 + ty;
-  const bool valid_ij = i < g.NX && j < g.NY;
   __syncthreads();
 
-  constexpr int NE = 8;
-  double t[NPT][NE][NDOF];
-  const bool active = valid_ij && kl0 + tzb < g.nzl;
-  if (active) {
-#pragma unroll
-    for (int p = 0; p < NPT; ++p)
-#pragma unroll
-      for (int e = 0; e < NE; ++e)
-#pragma unroll
-        for (int d = 0; d < NDOF; ++d) t[p][e][d] = 0.0;
-    // same (dk, dj, di) order per node as elem_kernel; the NPT nodes of a thread consume the same Ke constants in the
-    // same step, so one uniform-register load feeds NPT DFMAs
-#pragma unroll
-    for (int dk = -1; dk <= 1; ++dk)
-#pragma unroll
-      for (int dj = -1; dj <= 1; ++dj)
-#pragma unroll
-        for (int di = -1; di <= 1; ++di) {
-          double uv[NPT][NDOF];
-#pragma unroll
-          for (int p = 0; p < NPT; ++p) {
-            const double* up = &su[tzb + p + 1 + dk][ty + 1 + dj][(tx + 1 + di) * NDOF];
-#pragma unroll
-            for (int c = 0; c < NDOF; ++c) uv[p][c] = up[c];
-          }
-#pragma unroll
-          for (int e = 0; e < NE; ++e) {
-            const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
-            const int ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
-            const int bx = ax + di, by = ay + dj, bz = az + dk;
-            if (bx < 0 || bx > 1 || by < 0 || by > 1 || bz < 0 || bz > 1) continue;
-            const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
-#pragma unroll
-            for (int c = 0; c < NDOF; ++c)
-#pragma unroll
-              for (int d = 0; d < NDOF; ++d) {
-                const double kv = ke.v[(a * NDOF + d) * LD + bn * NDOF + c];
-#pragma unroll
-                for (int p = 0; p < NPT; ++p) t[p][e][d] = fma(kv, uv[p][c], t[p][e][d]);
-              }
-          }
-        }
-  }
+  const int tx = tid % BX, ty = tid / BX;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool valid = i < g.NX && j < g.NY;
+  const int c0 = (ty + 1) * ROWLEN + (tx + 1) * NDOF;  // this thread's node inside a staged plane
+  const int e0 = ty * (BX + 1) + tx;                    // its (ox, oy) = (0, 0) element inside a staged layer
+  const long long rrow = valid ? ((long long)j * g.NX + i) * NDOF : 0;  // dof offset of the node inside a plane
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-#pragma unroll
-  for (int p = 0; p < NPT; ++p) {
-    const int kl = kl0 + tzb + p;
-    if (active && kl < g.nzl) {
+
+  for (int kl = kA, t = 0; kl < kB; ++kl, ++t) {
+    const bool more = kl + 1 < kB;
+    // ---- issued now, landing during the FMA phase: next step's plane / layer (cp.async into the free ring slots) and
+    //      L1 prefetches of this step's epilogue operands (no registers held across the FMA phase)
+    unsigned char mk[NQ];
+    if (more) {
+      issue_plane(kl + 2, (t + 3) & 3, mk);  // slot held plane kl-2: last read in the previous step, which ended with a barrier
+      issue_layer(kl + 1, (t + 2) & 3);
+    }
+    const long long r0 = (long long)kl * xplane + rrow;
+    if (valid) {
+      if (MODE != EMODE_SPMV) prefetch_l1(b + r0), prefetch_l1(b + r0 + NDOF - 1);
+      if (MODE == EMODE_JACOBI) prefetch_l1(diag + r0), prefetch_l1(diag + r0 + NDOF - 1);
+      if (mask) prefetch_l1(mask + r0);
+    }
+    const double* pl[3] = {su[t & 3], su[(t + 1) & 3], su[(t + 2) & 3]};
+    const double* sl[2] = {ss[t & 3], ss[(t + 1) & 3]};
+    if (valid) {
+      // elements below the node plane (oz = 0: neighbour planes dk = -1, 0) then above it (oz = 1: dk = 0, 1): 12 live
+      // accumulators instead of 24; per element the (dk, dj, di) order of elem_kernel is kept, so y is bit-identical
       double acc[NDOF];
 #pragma unroll
       for (int d = 0; d < NDOF; ++d) acc[d] = 0.0;
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
-        const double se = ss[tzb + p + oz][ty + oy][tx + ox];
+      for (int oz = 0; oz < 2; ++oz) {
+        double tacc[4][NDOF];
 #pragma unroll
-        for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, t[p][e][d], acc[d]);
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int d = 0; d < NDOF; ++d) tacc[e][d] = 0.0;
+        const int az = 1 - oz;
+#pragma unroll
+        for (int dk = -az; dk <= 1 - az; ++dk)
+#pragma unroll
+          for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+            for (int di = -1; di <= 1; ++di) {
+              const double* up = pl[dk + 1] + c0 + dj * ROWLEN + di * NDOF;
+              double uv[NDOF];
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) uv[c] = up[c];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ox = e & 1, oy = (e >> 1) & 1;
+                const int ax = 1 - ox, ay = 1 - oy;
+                const int bx = ax + di, by = ay + dj, bz = az + dk;
+                if (bx < 0 || bx > 1 || by < 0 || by > 1) continue;
+                const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+#pragma unroll
+                for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+                  for (int d = 0; d < NDOF; ++d)
+                    tacc[e][d] = fma(ke.v[(a * NDOF + d) * LD + bn * NDOF + c], uv[c], tacc[e][d]);
+              }
+            }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ox = e & 1, oy = (e >> 1) & 1;
+          const double se = sl[oz][e0 + oy * (BX + 1) + ox];
+#pragma unroll
+          for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, tacc[e][d], acc[d]);
+        }
       }
-      const long long r0 = (((long long)kl * g.NY + j) * g.NX + i) * NDOF;
 #pragma unroll
       for (int d = 0; d < NDOF; ++d) {
         const long long r = r0 + d;
+        // unmasked rows: x is the centre value of the staged plane; Dirichlet rows (rare) re-read it from memory
         const bool mr = mask && __ldg(mask + r);
-        const double xr = __ldg(x + r);
+        const double xr = mr ? __ldg(x + r) : pl[1][c0 + d];
         const double ax = mr ? bcdiag * xr : acc[d];
         double out;
         if (MODE == EMODE_SPMV) out = ax;
@@ -343,12 +396,17 @@ __global__ void __launch_bounds__(32 * BY * BZT, MINB)
         else out = xr + w * ((__ldg(b + r) - ax) / __ldg(diag + r));
         y[r] = out;
         if (partials) {
-          const double dv = dotv ? __ldg(dotv + r) : 0.0;
+          const double dvv = dotv ? __ldg(dotv + r) : 0.0;
           d0 = fma(out, xr, d0);
-          d1 = fma(xr, dv, d1);
-          d2 = fma(out, dv, d2);
+          d1 = fma(xr, dvv, d1);
+          d2 = fma(out, dvv, d2);
         }
       }
+    }
+    if (more) {
+      cp_async_wait_all();
+      mask_plane((t + 3) & 3, mk);
+      __syncthreads();
     }
   }
   if (partials) {
@@ -374,36 +432,32 @@ static dim3 elem_grid(const Geo& g) {
   return dim3((g.NX + BX - 1) / BX, (g.NY + BY - 1) / BY, (g.nzl + BZ - 1) / BZ);
 }
 
-// ---- variant selection (3-D, ndof 1 or 3): 0 = one node per thread (elem_kernel); two nodes per thread with
-//      1 = 128-thread CTAs, 3 per SM (no register cap), 2 = 256-thread CTAs on a 32x4x4 brick, 2 per SM,
-//      3 = 128-thread CTAs, 4 per SM.  Chosen per process by pmb_elem_set_variant() / PMB_ELEM_VARIANT
-//      or measured by pmb_elem_autotune(); all variants produce bit-identical y.
-enum { PMB_ELEM_VARIANTS = 4 };
-static int g_elem_variant = -1;
-static int elem_variant() {
-  if (g_elem_variant < 0) {
+// ---- layout selection (3-D, ndof 1 or 3): 0 = one node per thread on a 32x4x2 brick (elem_kernel), 1 / 2 = z-marching
+//      32x8 / 32x4 columns with ring-buffered planes (elem_kernel_zm).  Chosen per process by pmb_elem_set_variant() /
+//      PMB_ELEM_VARIANT or measured by pmb_elem_autotune(); all layouts produce bit-identical y.
+enum { PMB_ELEM_VARIANTS = 3 };
+static int g_elem_variant[4] = {-1, -1, -1, -1};  // per dofs-per-node (the FMA phase is 9x heavier for ndof = 3 than for 1)
+static int& elem_variant(int ndof) {
+  if (g_elem_variant[0] < 0) {
     const char* e = getenv("PMB_ELEM_VARIANT");
-    g_elem_variant = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
+    const int v = (e && e[0] >= '0' && e[0] < '0' + PMB_ELEM_VARIANTS) ? e[0] - '0' : 0;
+    for (int i = 0; i < 4; ++i) g_elem_variant[i] = v;
   }
-  return g_elem_variant;
+  return g_elem_variant[ndof >= 1 && ndof <= 3 ? ndof : 0];
 }
 extern "C" int pmb_elem_set_variant(int v) {
   PMB_REQUIRE(v >= 0 && v < PMB_ELEM_VARIANTS, "pmb_elem_set_variant: variant %d not in 0..%d", v, PMB_ELEM_VARIANTS - 1);
-  g_elem_variant = v;
+  for (int i = 0; i < 4; ++i) g_elem_variant[i] = v;
   return 0;
 }
-extern "C" int pmb_elem_get_variant(void) { return elem_variant(); }
-
-template <int BY, int BZ>
-static dim3 elem_grid_v2(const Geo& g) {
-  return dim3((g.NX + 31) / 32, (g.NY + BY - 1) / BY, (g.nzl + BZ - 1) / BZ);
-}
+extern "C" int pmb_elem_get_variant(int ndof) { return elem_variant(ndof); }
+extern "C" int pmb_elem_num_variants(void) { return PMB_ELEM_VARIANTS; }
 
 static dim3 elem_grid_any(const Geo& g, int variant) {
   if (!g.dim3) return elem_grid<false>(g);
   switch (variant) {
-    case 1: case 3: return elem_grid_v2<4, 2>(g);
-    case 2: return elem_grid_v2<4, 4>(g);
+    case 1: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 7) / 8, (g.nzl + ZM_L - 1) / ZM_L);
+    case 2: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 3) / 4, (g.nzl + ZM_L - 1) / ZM_L);
   }
   return elem_grid<true>(g);
 }
@@ -426,16 +480,14 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
                        double* dot_out, double* ws, cudaStream_t st) {
   KeParam<NDOF, DIM3> ke;
   memcpy(ke.v, Ke_host, sizeof(ke.v));
-  const int variant = (DIM3 && NDOF != 2) ? elem_variant() : 0;
+  const int variant = (DIM3 && NDOF != 2) ? elem_variant(NDOF) : 0;
   dim3 grid = elem_grid_any(g, variant);
   double* part = dot_out ? ws : nullptr;
   if constexpr (DIM3 && NDOF != 2) {
     if (variant == 1)
-      elem_kernel_v2<NDOF, MODE, 4, 1, 2, 3><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+      elem_kernel_zm<NDOF, MODE, 8, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
     else if (variant == 2)
-      elem_kernel_v2<NDOF, MODE, 4, 2, 2, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
-    else if (variant == 3)
-      elem_kernel_v2<NDOF, MODE, 4, 1, 2, 4><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+      elem_kernel_zm<NDOF, MODE, 4, 4><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
     else
       elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
   } else {
@@ -489,7 +541,7 @@ extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const double* Ke_host,
 }
 
 // Time every variant of the 3-D matrix-free kernel on the caller's buffers (Jacobi mode, y is scratch) and keep the
-// fastest for this process.  ms_out[4] receives the average launch time of each variant.  Not capturable.
+// fastest for this process and this number of dofs per node.  ms_out[pmb_elem_num_variants()] receives the average launch time of each variant.  Not capturable.
 extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const double* s, const unsigned char* bcmask,
                                  double bcdiagval, const double* x, const double* b, const double* diag, double* y,
                                  double* ms_out, void* stream) {
@@ -498,11 +550,12 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return pmb_set_error("pmb_elem_autotune: cudaEventCreate failed");
-  const int saved = elem_variant();
+  int& slot = elem_variant(p->ndof);
+  const int saved = slot;
   int best = saved, rc = 0;
   float best_ms = 1e30f;
   for (int v = 0; v < PMB_ELEM_VARIANTS && !rc; ++v) {
-    g_elem_variant = v;
+    slot = v;
     const int reps = 6;
     for (int r = 0; r < 2 + reps && !rc; ++r) {
       if (r == 2) cudaEventRecord(e0, st);
@@ -518,6 +571,6 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  g_elem_variant = rc ? saved : best;
+  slot = rc ? saved : best;
   return rc;
 }

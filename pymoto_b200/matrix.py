@@ -33,11 +33,11 @@ class DeviceCSR:
     # attached its generator; the assembled values stay the source of truth for everything else.  Set to False to
     # stream the CSR values on every level.
     matrix_free = True
-    # The 3-D matrix-free kernel exists in several register / brick layouts (pmb_elem.cu, all bit-identical in y): on
+    # The 3-D matrix-free kernel exists in several layouts (pmb_elem.cu: brick / z-marching columns, bit-identical in y): on
     # operators of at least ``autotune_min_rows`` rows the first assembly times them once on its own operands and keeps
     # the fastest for the process (PMB_ELEM_VARIANT=<n> pins one instead; PMB_ELEM_AUTOTUNE=0 keeps variant 0).
     autotune_min_rows = 1_000_000
-    elem_timings_ms = None  # filled by the autotune pass: [ms per launch of every variant]
+    elem_timings_ms = {}  # filled by the autotune pass: ndof -> [ms per launch of every layout]
 
     def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None, comm=None, level=0):
         dv.require_cuda()
@@ -131,18 +131,18 @@ class DeviceCSR:
     def autotune_matrix_free(self):
         """Measure the matrix-free kernel variants on this operator (once per process); no-op when not applicable."""
         g, gen = self.grid, self.generator
-        if (DeviceCSR.elem_timings_ms is not None or gen is None or not DeviceCSR.matrix_free or g.nz == 0 or g.ndof == 2
+        if (g.ndof in DeviceCSR.elem_timings_ms or gen is None or not DeviceCSR.matrix_free or g.nz == 0 or g.ndof == 2
                 or self.n < DeviceCSR.autotune_min_rows or "PMB_ELEM_VARIANT" in os.environ
                 or os.environ.get("PMB_ELEM_AUTOTUNE", "1") == "0" or torch.cuda.is_current_stream_capturing()):
             return
         x, b, y = self.new_vec(zero=True), self.new_vec(zero=True), self.new_vec(zero=True)
         x.copy_(torch.rand(self.n, dtype=torch.float64, device=x.device))
-        ms = (C.c_double * 4)()
+        ms = (C.c_double * _lib.query("pmb_elem_num_variants"))()
         mask = gen["mask"]
         _lib.call("pmb_elem_autotune", g, gen["ke"].ctypes.data, gen["s"].data_ptr(), None if mask is None else mask.data_ptr(),
                   float(gen["bcdiag"]), x.data_ptr(), b.data_ptr(), self.diagonal_device().data_ptr(), y.data_ptr(),
                   C.addressof(ms), dv.stream())
-        DeviceCSR.elem_timings_ms = [float(v) for v in ms]
+        DeviceCSR.elem_timings_ms[g.ndof] = [float(v) for v in ms]
 
     # ---- products
     def _launch(self, gen, grid, mode, data_ptr, s_ptr, mask_ptr, x_ptr, b_ptr, diag_ptr, w, y_ptr, dotv_ptr, dot_ptr, ws_ptr):

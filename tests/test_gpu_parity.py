@@ -454,10 +454,10 @@ def test_matrix_free_operator_equals_assembled(pmb, shape, ndof):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3)])
+@pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3), ((5, 20, 19), 3), ((34, 9, 17), 2)])
 def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
-    """Every register / brick layout of the 3-D matrix-free kernel (pmb_elem_set_variant 1..3: two nodes per thread)
-    must reproduce variant 0 bit for bit in y (same products, same order per node) for all modes, on the whole grid and
+    """Every layout of the 3-D matrix-free kernel (pmb_elem_set_variant 1, 2: z-marching columns with ring-buffered
+    planes) must reproduce variant 0 (one node per thread on a brick) bit for bit in y (same products, same order per node) for all modes, on the whole grid and
     on sub-slabs with odd plane counts; the fused dot products agree to rounding.  The autotune entry point runs, returns
     one time per variant and leaves a valid selection."""
     import ctypes as C
@@ -475,12 +475,14 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     n = K.shape[0]
     vd, bd = dv.to_device(rng.standard_normal(n)), dv.to_device(rng.standard_normal(n))
     D = K.diagonal_device()
-    saved = _lib.query("pmb_elem_get_variant")
+    saved = _lib.query("pmb_elem_get_variant", ndof)
     try:
         ref = {}
-        for variant in range(4):
+        nvar = _lib.query("pmb_elem_num_variants")
+        assert nvar >= 3
+        for variant in range(nvar):
             _lib.call("pmb_elem_set_variant", variant)
-            assert _lib.query("pmb_elem_get_variant") == variant
+            assert _lib.query("pmb_elem_get_variant", ndof) == variant
             for mode in (_lib.SPMV, _lib.RESIDUAL, _lib.JACOBI):
                 out, d3 = dv.zeros(n), dv.empty(3)
                 K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
@@ -504,12 +506,12 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
             want = np.zeros(n)
             want[k0 * plane:(k0 + npl) * plane] = ref[_lib.JACOBI][0][k0 * plane:(k0 + npl) * plane]
             assert np.array_equal(got, want), ("slab", variant)
-        ms = (C.c_double * 4)()
+        ms = (C.c_double * nvar)()
         scratch = dv.zeros(n)
         _lib.call("pmb_elem_autotune", K.grid, gen["ke"].ctypes.data, gen["s"].data_ptr(), gen["mask"].data_ptr(),
                   float(gen["bcdiag"]), vd.data_ptr(), bd.data_ptr(), D.data_ptr(), scratch.data_ptr(), C.addressof(ms), dv.stream())
         assert all(0.0 < t < 1e3 for t in ms)
-        assert 0 <= _lib.query("pmb_elem_get_variant") < 4
+        assert 0 <= _lib.query("pmb_elem_get_variant", ndof) < nvar
         assert np.array_equal(scratch.cpu().numpy(), ref[_lib.JACOBI][0])
     finally:
         _lib.call("pmb_elem_set_variant", saved)
