@@ -111,7 +111,8 @@ int pmb_elem_spmv(const pmb_grid* g, int mode, const double* Ke_host, const doub
                   const double* dotv, double* dot_out, double* ws, void* stream);
 long long pmb_elem_ws_doubles(const pmb_grid* g);
 /* The 3-D kernel behind pmb_elem_spmv exists in pmb_elem_num_variants() layouts (0 = one node per thread on a 32x4x2
- * brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered planes; y is bit-identical for all).  set pins the layout for this process, get reads the one used for `ndof` dofs per node (initially PMB_ELEM_VARIANT or
+ * brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered planes, bit-identical y; 3 = FP64 tensor-core (DMMA)
+ * layout for ndof = 3, y equal to rounding).  set pins the layout for this process, get reads the one used for `ndof` dofs per node (initially PMB_ELEM_VARIANT or
  * 0);
  * pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's operands, stores the launch times in
  * ms_out[pmb_elem_num_variants()] and keeps the fastest for that ndof.  Not capturable into a CUDA graph. */

@@ -426,6 +426,252 @@ __global__ void __launch_bounds__(32 * BY, MINB)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core layout (3-D, ndof = 3): the element products Ke u_e as FP64 DMMA (mma.sync m8n8k4).
+//
+// The layouts above issue one DFMA per multiply-add plus ~0.5 uniform constant loads and shared-memory loads around it:
+// they saturate the instruction issue / operand delivery long before the FP64 pipe (45-50 % busy).  DMMA.8x8x4 runs at
+// the same 37 TFLOP/s (scripts/probe_dmma.cu) with 8x fewer instructions and keeps Ke in registers: for 8 elements at a
+// time a warp forms T = Ke (24 x 24) x U (24 x 8) as 3 x 6 DMMAs, the 18 A fragments (Ke) held in registers (read once
+// from a shared-memory copy: lane-indexed reads of the parameter constant bank serialise 32-fold and the compiler
+// re-materialises them inside the loop), the B fragments (element displacements) read straight from the staged node
+// planes.  A CTA owns a column of 31 x 7 nodes = 32 x 8 elements per layer and marches over the element layers (same
+// cp.async plane ring as elem_kernel_zm): per layer the 8 warps write s_e T_e to shared memory, then one thread per node
+// gathers the 4 + 4 element contributions (the upper four are carried to the next step in registers) and applies the
+// epilogue.  Summation order differs from
+// elem_kernel (tensor-core accumulation, per-element grouping), so y agrees to rounding, not bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MM_EX = 32, MM_EY = 8, MM_NXT = MM_EX - 1, MM_NYT = MM_EY - 1;   // elements / owned nodes of a CTA per layer
+constexpr int MM_NT = 256, MM_NEL = MM_EX * MM_EY;                              // 8 warps x 4 batches of 8 elements
+constexpr int MM_SX = MM_EX + 1, MM_SY = MM_EY + 1, MM_ROW = MM_SX * 3;         // staged node plane: 33 x 9 nodes
+constexpr int MM_PLANE = (MM_SY * MM_ROW + 1) / 2 * 2, MM_TLD = MM_NEL + 8;     // T row stride: 64 B shift between rows
+constexpr int MM_SMEM_DOUBLES = 3 * MM_PLANE + 2 * MM_NEL + 24 * MM_TLD;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MM_NT, 2)
+    elem_kernel_mma(Geo g, const __grid_constant__ KeParam<3, true> ke, int zl, const double* __restrict__ s,
+                    const unsigned char* __restrict__ mask, double bcdiag, const double* __restrict__ x,
+                    const double* __restrict__ b, const double* __restrict__ diag, double w, double* __restrict__ y,
+                    const double* __restrict__ dotv, double* __restrict__ partials) {
+  constexpr int NDOF = 3, NT = MM_NT;
+  constexpr int NQ = (MM_SY * MM_ROW + NT - 1) / NT;
+  extern __shared__ __align__(16) double smm[];
+  double* su = smm;                         // [3][MM_PLANE] ring of masked x planes
+  double* ss = smm + 3 * MM_PLANE;          // [2][MM_NEL]   element densities of the current / next layer
+  double* sT = ss + 2 * MM_NEL;             // [24][MM_TLD]  s_e (Ke u_e), row = local dof, column = element
+  __shared__ double wred[3][NT / 32];
+  __shared__ double sKe[24 * 24];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * MM_NXT, j0 = blockIdx.y * MM_NYT;   // first owned node of the column
+  for (int p = tid; p < 24 * 24; p += NT) sKe[p] = ke.v[p];
+  __syncthreads();
+  const int kA = blockIdx.z * zl, kB = min(kA + zl, g.nzl);       // owned local planes [kA, kB)
+  const long long xplane = (long long)g.NX * g.NY * NDOF, slayer = (long long)g.nx * g.ny;
+
+  // ---- A fragments: Ke[8 mt + lane/4][4 ks + lane%4], loaded once
+  double af[3][6];
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) af[mt][ks] = sKe[(8 * mt + (lane >> 2)) * 24 + 4 * ks + (lane & 3)];
+  // ---- B fragment offsets inside a staged plane: local dof kk = 4 ks + lane%4 = 3 b + c, node b = (bx, by, bz = ks >= 3)
+  int boff[6];
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks) {
+    const int kk = 4 * ks + (lane & 3), bn = kk / 3, c = kk - 3 * bn;
+    boff[ks] = ((bn >> 1) & 1) * MM_ROW + (bn & 1) * NDOF + c;
+  }
+  // ---- staging slots (computed once): staged node (sx, sy) = global node (i0 - 1 + sx, j0 - 1 + sy)
+  int xoff[NQ];
+  bool xok[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int p = tid + NT * q;
+    const int row = p / MM_ROW, col = p - row * MM_ROW;
+    const int i = i0 - 1 + col / NDOF, j = j0 - 1 + row;
+    xok[q] = p < MM_SY * MM_ROW && i >= 0 && i < g.NX && j >= 0 && j < g.NY;
+    xoff[q] = (j * g.NX + (i0 - 1)) * NDOF + col;
+  }
+  const int sex = tid % MM_EX, sey = tid / MM_EX;               // this thread stages the density of tile element tid
+  const int sei = i0 - 1 + sex, sej = j0 - 1 + sey;
+  const bool sokk = sei >= 0 && sei < g.nx && sej >= 0 && sej < g.ny;
+  const int soff = sej * g.nx + sei;
+  auto plane_ok = [&](int kl) {
+    const int k = g.kz0 + kl;
+    return k >= 0 && k < g.NZ && kl <= g.nzl;
+  };
+  auto layer_ok = [&](int el) {
+    const int ek = g.kz0 + el;
+    return ek >= 0 && ek < g.nzE && el < g.nzl;
+  };
+  // x plane kl -> ring slot by cp.async (zero-fill outside the grid); the Dirichlet mask bytes are only prefetched to L1
+  // here and applied by mask_plane once the copies have landed (no register carries them across the DMMA phase)
+  auto issue_plane = [&](int kl, int slot) {
+    const bool pok = plane_ok(kl);
+    const double* xp = x + (long long)kl * xplane;
+    const unsigned char* mp = mask + (long long)kl * xplane;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int p = tid + NT * q;
+      const bool ok = pok && xok[q];
+      if (p < MM_SY * MM_ROW) cp_async8(su + slot * MM_PLANE + p, ok ? xp + xoff[q] : x, ok);
+      if (mask && ok) prefetch_l1(mp + xoff[q]);
+    }
+  };
+  auto mask_plane = [&](int kl, int slot) {
+    if (!mask || !plane_ok(kl)) return;
+    const unsigned char* mp = mask + (long long)kl * xplane;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      if (xok[q] && __ldg(mp + xoff[q])) su[slot * MM_PLANE + tid + NT * q] = 0.0;
+  };
+  auto issue_layer = [&](int el, int slot) {
+    const bool ok = layer_ok(el) && sokk;
+    cp_async8(ss + slot * MM_NEL + tid, ok ? s + (long long)el * slayer + soff : s, ok);
+  };
+
+  // ---- prime: planes kA-1, kA -> ring slots 0, 1; layer kA-1 -> density slot 0
+  issue_plane(kA - 1, 0);
+  issue_plane(kA, 1);
+  issue_layer(kA - 1, 0);
+  cp_async_wait_all();
+  mask_plane(kA - 1, 0);
+  mask_plane(kA, 1);
+  __syncthreads();
+
+  // gather role: one thread per owned node of the column
+  const int nx = tid % MM_NXT, ny = tid / MM_NXT;
+  const int gi = i0 + nx, gj = j0 + ny;
+  const bool valid = ny < MM_NYT && gi < g.NX && gj < g.NY;
+  const long long rrow = valid ? ((long long)gj * g.NX + gi) * NDOF : 0;
+  const int ecol = ny * MM_EX + nx;  // element (ox, oy) = (0, 0) of this node in the tile; (ox, oy) adds ox + oy * MM_EX
+  double hi[NDOF] = {0.0, 0.0, 0.0};
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+
+  for (int L = kA - 1, t = 0; L < kB; ++L, ++t) {
+    const bool more = L + 1 < kB;
+    if (more) {  // next layer needs node plane L+2 and densities L+1: in flight during the DMMA phase
+      issue_plane(L + 2, (t + 2) % 3);
+      issue_layer(L + 1, (t + 1) & 1);
+    }
+    const long long r0 = (long long)L * xplane + rrow;  // rows of this thread's node in plane L (owned iff L >= kA)
+    if (valid && L >= kA) {
+      if (MODE != EMODE_SPMV) prefetch_l1(b + r0), prefetch_l1(b + r0 + NDOF - 1);
+      if (MODE == EMODE_JACOBI) prefetch_l1(diag + r0), prefetch_l1(diag + r0 + NDOF - 1);
+      if (mask) prefetch_l1(mask + r0);
+    }
+    const double* pl0 = su + (t % 3) * MM_PLANE;        // node plane L   (bottom face of the layer's elements)
+    const double* pl1 = su + ((t + 1) % 3) * MM_PLANE;  // node plane L+1 (top face)
+    const double* sl = ss + (t & 1) * MM_NEL;
+
+    // ---- DMMA phase: warp w takes the element batches w, w + 8, w + 16, w + 24 of the layer
+#pragma unroll 1
+    for (int bt = warp; bt < MM_NEL / 8; bt += NT / 32) {
+      const int e = bt * 8 + (lane >> 2);            // B-fragment column of this lane
+      const int ebase = (e / MM_EX) * MM_ROW + (e % MM_EX) * NDOF;
+      double c[3][2];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) c[mt][0] = c[mt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) {
+        const double bv = (ks < 3 ? pl0 : pl1)[ebase + boff[ks]];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) dmma884(c[mt][0], c[mt][1], af[mt][ks], bv);
+      }
+      const int e0 = bt * 8 + 2 * (lane & 3);        // C-fragment columns e0, e0 + 1; rows 8 mt + lane/4
+      const double2 sv = *reinterpret_cast<const double2*>(sl + e0);
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+        *reinterpret_cast<double2*>(sT + (8 * mt + (lane >> 2)) * MM_TLD + e0) = make_double2(sv.x * c[mt][0], sv.y * c[mt][1]);
+    }
+    __syncthreads();
+
+    // ---- gather: node plane L takes the az = 0 rows of its four elements in layer L plus `hi` from layer L-1;
+    //      the az = 1 rows are the contribution of layer L to node plane L+1
+    if (valid) {
+      double lo[NDOF], up[NDOF];
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) lo[d] = hi[d], up[d] = 0.0;
+#pragma unroll
+      for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+          const double* tp = sT + ecol + oy * MM_EX + ox;
+          const int a0 = (1 - ox) + 2 * (1 - oy);
+#pragma unroll
+          for (int d = 0; d < NDOF; ++d) {
+            lo[d] += tp[(a0 * NDOF + d) * MM_TLD];
+            up[d] += tp[((a0 + 4) * NDOF + d) * MM_TLD];
+          }
+        }
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) hi[d] = up[d];
+      if (L >= kA) {
+        const int c0 = (ny + 1) * MM_ROW + (nx + 1) * NDOF;  // this node inside staged plane L
+#pragma unroll
+        for (int d = 0; d < NDOF; ++d) {
+          const long long r = r0 + d;
+          const bool mr = mask && __ldg(mask + r);
+          const double xr = mr ? __ldg(x + r) : pl0[c0 + d];
+          const double ax = mr ? bcdiag * xr : lo[d];
+          double out;
+          if (MODE == EMODE_SPMV) out = ax;
+          else if (MODE == EMODE_RESID) out = __ldg(b + r) - ax;
+          else out = xr + w * ((__ldg(b + r) - ax) / __ldg(diag + r));
+          y[r] = out;
+          if (partials) {
+            const double dvv = dotv ? __ldg(dotv + r) : 0.0;
+            d0 = fma(out, xr, d0);
+            d1 = fma(xr, dvv, d1);
+            d2 = fma(out, dvv, d2);
+          }
+        }
+      }
+    }
+    if (more) {
+      cp_async_wait_all();
+      mask_plane(L + 2, (t + 2) % 3);
+    }
+    __syncthreads();  // T may be overwritten, the next plane / layer are visible
+  }
+  if (partials) {
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (lane == 0) wred[0][warp] = d0, wred[1][warp] = d1, wred[2][warp] = d2;
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int v = 0; v < NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
+      const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      partials[3 * bid] = s0;
+      partials[3 * bid + 1] = s1;
+      partials[3 * bid + 2] = s2;
+    }
+  }
+}
+
+// planes per CTA of the tensor-core layout: few enough CTAs per wave lost to the tail, little redundant layer work
+// (every CTA computes one extra element layer)
+static int mma_zl(const Geo& g) {
+  const long long tiles = (long long)((g.NX + MM_NXT - 1) / MM_NXT) * ((g.NY + MM_NYT - 1) / MM_NYT);
+  const long long slots = 2LL * 148;
+  int best = 8;
+  double best_cost = 1e300;
+  for (int zl = 4; zl <= 32; ++zl) {
+    const long long ctas = tiles * ((g.nzl + zl - 1) / zl);
+    const long long waves = (ctas + slots - 1) / slots;
+    const double cost = (double)waves * slots / (double)ctas * (zl + 1.0) / zl;  // tail loss x extra-layer overhead
+    if (cost < best_cost - 1e-12) best_cost = cost, best = zl;
+  }
+  return best < g.nzl ? best : (g.nzl > 0 ? g.nzl : 1);
+}
+
 template <bool DIM3>
 static dim3 elem_grid(const Geo& g) {
   constexpr int BX = 32, BY = DIM3 ? 4 : 8, BZ = DIM3 ? 2 : 1;
@@ -433,9 +679,10 @@ static dim3 elem_grid(const Geo& g) {
 }
 
 // ---- layout selection (3-D, ndof 1 or 3): 0 = one node per thread on a 32x4x2 brick (elem_kernel), 1 / 2 = z-marching
-//      32x8 / 32x4 columns with ring-buffered planes (elem_kernel_zm).  Chosen per process by pmb_elem_set_variant() /
+//      32x8 / 32x4 columns with ring-buffered planes (elem_kernel_zm), 3 = FP64 tensor-core layout (elem_kernel_mma,
+//      ndof 3 only; other ndof fall back to 0).  Chosen per process by pmb_elem_set_variant() /
 //      PMB_ELEM_VARIANT or measured by pmb_elem_autotune(); all layouts produce bit-identical y.
-enum { PMB_ELEM_VARIANTS = 3 };
+enum { PMB_ELEM_VARIANTS = 4 };
 static int g_elem_variant[4] = {-1, -1, -1, -1};  // per dofs-per-node (the FMA phase is 9x heavier for ndof = 3 than for 1)
 static int& elem_variant(int ndof) {
   if (g_elem_variant[0] < 0) {
@@ -458,6 +705,11 @@ static dim3 elem_grid_any(const Geo& g, int variant) {
   switch (variant) {
     case 1: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 7) / 8, (g.nzl + ZM_L - 1) / ZM_L);
     case 2: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 3) / 4, (g.nzl + ZM_L - 1) / ZM_L);
+    case 3:
+      if (g.ndof == 3) {
+        const int zl = mma_zl(g);
+        return dim3((g.NX + MM_NXT - 1) / MM_NXT, (g.NY + MM_NYT - 1) / MM_NYT, (g.nzl + zl - 1) / zl);
+      }
   }
   return elem_grid<true>(g);
 }
@@ -488,6 +740,18 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
       elem_kernel_zm<NDOF, MODE, 8, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
     else if (variant == 2)
       elem_kernel_zm<NDOF, MODE, 4, 4><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+    else if (variant == 3 && NDOF == 3) {
+      if constexpr (NDOF == 3) {
+        constexpr size_t smem = sizeof(double) * MM_SMEM_DOUBLES;
+        static bool configured = false;
+        if (!configured) {
+          cudaError_t e = cudaFuncSetAttribute(elem_kernel_mma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return pmb_set_error("elem_kernel_mma attribute: %s", cudaGetErrorString(e));
+          configured = true;
+        }
+        elem_kernel_mma<MODE><<<grid, MM_NT, smem, st>>>(g, ke, mma_zl(g), s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+      }
+    }
     else
       elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
   } else {

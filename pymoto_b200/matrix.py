@@ -129,9 +129,10 @@ class DeviceCSR:
         return self.diagonal_device().cpu().numpy()
 
     def autotune_matrix_free(self):
-        """Measure the matrix-free kernel variants on this operator (once per process); no-op when not applicable."""
+        """Measure the matrix-free kernel layouts on this operator (once per process and dofs per node); no-op when not
+        applicable (2-D, small operators, slab-decomposed runs: every rank must run the same layout there)."""
         g, gen = self.grid, self.generator
-        if (g.ndof in DeviceCSR.elem_timings_ms or gen is None or not DeviceCSR.matrix_free or g.nz == 0 or g.ndof == 2
+        if (g.ndof in DeviceCSR.elem_timings_ms or gen is None or self.comm is not None or not DeviceCSR.matrix_free or g.nz == 0 or g.ndof == 2
                 or self.n < DeviceCSR.autotune_min_rows or "PMB_ELEM_VARIANT" in os.environ
                 or os.environ.get("PMB_ELEM_AUTOTUNE", "1") == "0" or torch.cuda.is_current_stream_capturing()):
             return

@@ -456,8 +456,8 @@ def test_matrix_free_operator_equals_assembled(pmb, shape, ndof):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3), ((5, 20, 19), 3), ((34, 9, 17), 2)])
 def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
-    """Every layout of the 3-D matrix-free kernel (pmb_elem_set_variant 1, 2: z-marching columns with ring-buffered
-    planes) must reproduce variant 0 (one node per thread on a brick) bit for bit in y (same products, same order per node) for all modes, on the whole grid and
+    """Every layout of the 3-D matrix-free kernel must reproduce variant 0 (one node per thread on a brick): the z-marching
+    columns (1, 2) bit for bit, the FP64 tensor-core layout (3; DMMA accumulation order) to 1e-11 of the field magnitude in y (same products, same order per node) for all modes, on the whole grid and
     on sub-slabs with odd plane counts; the fused dot products agree to rounding.  The autotune entry point runs, returns
     one time per variant and leaves a valid selection."""
     import ctypes as C
@@ -479,7 +479,7 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     try:
         ref = {}
         nvar = _lib.query("pmb_elem_num_variants")
-        assert nvar >= 3
+        assert nvar >= 4
         for variant in range(nvar):
             _lib.call("pmb_elem_set_variant", variant)
             assert _lib.query("pmb_elem_get_variant", ndof) == variant
@@ -487,11 +487,15 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
                 out, d3 = dv.zeros(n), dv.empty(3)
                 K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
                 got = (out.cpu().numpy(), d3.cpu().numpy())
+                exact = variant in (1, 2) or ndof != 3
                 if variant == 0:
                     ref[mode] = got
-                else:
+                elif exact:
                     assert np.array_equal(got[0], ref[mode][0]), (variant, mode)
                     np.testing.assert_allclose(got[1], ref[mode][1], rtol=1e-11, atol=1e-9)
+                else:
+                    np.testing.assert_allclose(got[0], ref[mode][0], rtol=0, atol=1e-11 * max(1.0, np.abs(ref[mode][0]).max()))
+                    np.testing.assert_allclose(got[1], ref[mode][1], rtol=1e-10, atol=1e-8)
             # a sub-slab [k0, k0 + 3) of the same operator: pointers move with the slab, halo planes are read around it
             g, k0, npl = K.grid, 1, 3
             sg = make_grid(g.nx, g.ny, g.nz, g.ndof, k0, npl)
@@ -505,14 +509,17 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
             got = out.cpu().numpy()
             want = np.zeros(n)
             want[k0 * plane:(k0 + npl) * plane] = ref[_lib.JACOBI][0][k0 * plane:(k0 + npl) * plane]
-            assert np.array_equal(got, want), ("slab", variant)
+            if exact:
+                assert np.array_equal(got, want), ("slab", variant)
+            else:
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * max(1.0, np.abs(want).max()))
         ms = (C.c_double * nvar)()
         scratch = dv.zeros(n)
         _lib.call("pmb_elem_autotune", K.grid, gen["ke"].ctypes.data, gen["s"].data_ptr(), gen["mask"].data_ptr(),
                   float(gen["bcdiag"]), vd.data_ptr(), bd.data_ptr(), D.data_ptr(), scratch.data_ptr(), C.addressof(ms), dv.stream())
         assert all(0.0 < t < 1e3 for t in ms)
         assert 0 <= _lib.query("pmb_elem_get_variant", ndof) < nvar
-        assert np.array_equal(scratch.cpu().numpy(), ref[_lib.JACOBI][0])
+        np.testing.assert_allclose(scratch.cpu().numpy(), ref[_lib.JACOBI][0], rtol=0, atol=1e-11 * max(1.0, np.abs(ref[_lib.JACOBI][0]).max()))
     finally:
         _lib.call("pmb_elem_set_variant", saved)
 
