@@ -89,3 +89,113 @@ def oc_update(x, dg, move=0.1, xmin=0.0, xmax=1.0, maxvol=None, l1=0.0, l2=10000
         xnew[:] = np.clip(x * np.sqrt(-dg / lmid), lb, ub)
         l1, l2 = (lmid, l2) if np.sum(xnew) - maxvol * x.size > 0 else (l1, lmid)
     return xnew
+
+
+# ------------------------------------------------------------------------------------------------------------------ MMA
+class MMAOracle:
+    """numpy restatement of the reference's MMA design update (pymoto/common/mma.py; test infrastructure only).
+
+      asymptote offsets   mma.py:120-140    mmasub (bounds, P, Q, rhs)   mma.py:170-244
+      subsolv             mma.py:246-474    (primal-dual Newton with the (m+1)x(m+1) reduced system and a residual line search)
+
+    Supports MMA1987 / MMA2007 (not GCMMA), scalar or vector xmin / xmax / move; ``step(x, g, dg)`` takes the responses
+    g (first = objective) and their sensitivities dg (rows) and returns the new design."""
+
+    def __init__(self, n, nresp, move=0.1, xmin=0.0, xmax=1.0, version="MMA2007", a0=1.0, epsimin=1e-10, ccoef=1e3, albefa=0.1,
+                 asyinit=0.5, asyincr=1.2, asydecr=0.7, asybound=10.0):
+        self.n, self.m = n, max(1, nresp - 1)
+        self.move, self.xmin, self.xmax = move, xmin * np.ones(n), xmax * np.ones(n)
+        self.dx = self.xmax - self.xmin
+        self.version = version
+        self.a0, self.epsimin, self.albefa = a0, epsimin, albefa
+        self.asyincr, self.asydecr, self.asybound = asyincr, asydecr, asybound
+        self.offset = asyinit * np.ones(n)
+        self.a, self.c, self.d = np.zeros(self.m), np.full(self.m, float(ccoef)), np.ones(self.m)
+        self.xold1 = self.xold2 = None
+        self.newton_iterations = 0
+
+    def step(self, x, g, dg):
+        g, dg = np.atleast_1d(np.asarray(g, dtype=float)), np.atleast_2d(np.asarray(dg, dtype=float))
+        if self.xold1 is not None and self.xold2 is not None:  # :120-140
+            zzz = (x - self.xold1) * (self.xold1 - self.xold2)
+            self.offset[zzz > 0] *= self.asyincr
+            self.offset[zzz < 0] *= self.asydecr
+            self.offset = np.clip(self.offset, 1 / self.asybound ** 2, self.asybound)
+        xnew = self._mmasub(x, g, dg, rho=1e-5)
+        self.xold2, self.xold1 = self.xold1, x.copy()
+        return xnew
+
+    def _mmasub(self, xval, g, dg, rho):
+        if g.size == 1:  # :172-175 dummy constraint
+            g, dg = np.hstack((g, -1.0)), np.vstack((dg, np.zeros(self.n)))
+        shift = self.offset * self.dx
+        self.low, self.upp = xval - shift, xval + shift
+        alfa = np.maximum.reduce([self.low + self.albefa * shift, xval - self.move * self.dx, self.xmin])
+        beta = np.minimum.reduce([self.upp - self.albefa * shift, xval + self.move * self.dx, self.xmax])
+        gp, gm, dx2 = np.maximum(dg, 0), np.maximum(-dg, 0), shift ** 2
+        if "1987" in self.version:
+            P, Q = dx2 * gp, dx2 * gm
+        else:
+            P = dx2 * (1.001 * gp + 0.001 * gm + rho / self.dx)
+            Q = dx2 * (0.001 * gp + 1.001 * gm + rho / self.dx)
+        rhs = P @ (1 / shift) + Q @ (1 / shift) - g
+        return self._subsolv(self.epsimin * np.sqrt(self.m + self.n), self.low, self.upp, alfa, beta, P, Q, rhs[1:], xval)
+
+    def _subsolv(self, epsimin, low, upp, alfa, beta, P, Q, b, x0):
+        m, a0, a, c, d = self.m, self.a0, self.a, self.c, self.d
+        P0, Q0, P1, Q1 = P[0], Q[0], P[1:], Q[1:]
+        x = np.clip(x0, alfa + 1e-10, beta - 1e-10)
+        y, z, lam, s = np.ones(m), 1.0, np.ones(m), np.ones(m)
+        xsi, eta = np.maximum(1.0 / (x - alfa), 1), np.maximum(1.0 / (beta - x), 1)
+        mu, zet = np.maximum(1, 0.5 * c), 1.0
+
+        def residual(x, y, z, lam, xsi, eta, mu, zet, s, epsi):
+            ux1, xl1 = upp - x, x - low
+            plam, qlam = P0 + lam @ P1, Q0 + lam @ Q1
+            gvec = P1 @ (1 / ux1) + Q1 @ (1 / xl1)
+            dpsidx = plam / ux1 ** 2 - qlam / xl1 ** 2
+            return np.concatenate([dpsidx - xsi + eta, c + d * y - mu - lam, [a0 - zet - a @ lam], gvec - a * z - y + s - b,
+                                   xsi * (x - alfa) - epsi, eta * (beta - x) - epsi, mu * y - epsi, [zet * z - epsi], lam * s - epsi])
+
+        epsi, self.newton_iterations = 1.0, 0
+        while epsi > epsimin:
+            r2 = residual(x, y, z, lam, xsi, eta, mu, zet, s, epsi) ** 2
+            rnorm, rmax, it = r2.sum(), r2.max(), 0
+            while rmax > (0.9 * epsi) ** 2 and it < 400:
+                it += 1
+                self.newton_iterations += 1
+                ux1, xl1 = upp - x, x - low
+                plam, qlam = P0 + lam @ P1, Q0 + lam @ Q1
+                gvec = P1 @ (1 / ux1) + Q1 @ (1 / xl1)
+                GG = P1 / ux1 ** 2 - Q1 / xl1 ** 2
+                delx = plam / ux1 ** 2 - qlam / xl1 ** 2 - epsi / (x - alfa) + epsi / (beta - x)
+                dely, delz = c + d * y - lam - epsi / y, a0 - a @ lam - epsi / z
+                dellam = gvec - a * z - y - b + epsi / lam
+                diagx = 2 * (plam / ux1 ** 3 + qlam / xl1 ** 3) + xsi / (x - alfa) + eta / (beta - x)
+                diagy = d + mu / y
+                AA = np.zeros((m + 1, m + 1))
+                AA[:m, :m] = np.diag(s / lam + 1.0 / diagy) + (GG / diagx) @ GG.T
+                AA[m, :m] = AA[:m, m] = a
+                AA[m, m] = -zet / z
+                sol = np.linalg.solve(AA, np.concatenate([dellam + dely / diagy - GG @ (delx / diagx), [delz]]))
+                dlam, dz = sol[:m], sol[m]
+                dx = -delx / diagx - (dlam @ GG) / diagx
+                dy = -dely / diagy + dlam / diagy
+                dxsi = -xsi + epsi / (x - alfa) - xsi * dx / (x - alfa)
+                deta = -eta + epsi / (beta - x) + eta * dx / (beta - x)
+                dmu, dzet, ds = -mu + epsi / y - mu * dy / y, -zet + epsi / z - zet * dz / z, -s + epsi / lam - s * dlam / lam
+                stmxx = -1.01 * min(np.min(dy / y), dz / z, np.min(dlam / lam), np.min(dxsi / xsi), np.min(deta / eta),
+                                    np.min(dmu / mu), dzet / zet, np.min(ds / s))
+                steg = 1.0 / max(-1.01 * np.min(dx / (x - alfa)), 1.01 * np.max(dx / (beta - x)), stmxx, 1.0)
+                old = (x, y, z, lam, xsi, eta, mu, zet, s)
+                step = (dx, dy, dz, dlam, dxsi, deta, dmu, dzet, ds)
+                for _ in range(400):
+                    x, y, z, lam, xsi, eta, mu, zet, s = (o + steg * dv_ for o, dv_ in zip(old, step))
+                    r2 = residual(x, y, z, lam, xsi, eta, mu, zet, s, epsi) ** 2
+                    if r2.sum() < rnorm:
+                        break
+                    steg /= 2
+                rnorm, rmax = r2.sum(), r2.max()
+            epsi /= 10
+        self.lam = lam
+        return x

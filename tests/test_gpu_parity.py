@@ -919,3 +919,39 @@ def test_write_to_vti_from_device_tensors(pmb, name, tmp_path):
         files = sorted(os.listdir(tmp_path / "out"))
         assert files == ["dat.0000.vti", "dat.0002.vti"], files
         assert np.array_equal(np.frombuffer(open(tmp_path / "out" / files[1], "rb").read(), dtype=np.uint8), want)
+
+
+@pytest.mark.parametrize("n,m", [(200_000, 1), (60_001, 2)])
+def test_mma_device_vs_oracle_larger_problem(pmb, n, m):
+    """Three successive device MMA updates against the numpy oracle (oracle/nextrows.MMAOracle, itself pinned to the
+    reference's fixtures) on a seeded problem larger than the fixtures: designs agree to 1e-7, asymptote offsets to rounding
+    apart from sign flips of variables that did not move, the multi-block reductions (n > 592 x 256) are exercised."""
+    from oracle.nextrows import MMAOracle
+    from pymoto_b200 import device as dv
+    from pymoto_b200.optimizers import MmaDeviceOps, mma_design_update
+
+    rng = np.random.default_rng(n)
+    wgt = 1.0 + rng.random(n)
+    cons = [np.full(n, 1.0 / n)] + [rng.random(n) / n for _ in range(m - 1)]
+
+    def responses(x):
+        g = [np.sum(wgt / (x + 0.05)) / n] + [c @ x - 0.4 * c.sum() for c in cons]
+        dg = [-wgt / (x + 0.05) ** 2 / n] + [c.copy() for c in cons]
+        return np.array(g), np.array(dg)
+
+    x0 = np.full(n, 0.4)
+    o = MMAOracle(n, m + 1)
+    ops = MmaDeviceOps(n, m)
+    offset = dv.to_device(np.full(n, 0.5))
+    opt = dict(albefa=0.1, asyincr=1.2, asydecr=0.7, asybound=10.0, a0=1.0, epsimin=1e-10, rho=1e-5, version=2007,
+               a=np.zeros(m), c=np.full(m, 1e3), d=np.ones(m))
+    xo, xd, xold1, xold2 = x0.copy(), dv.to_device(x0), None, None
+    for it in range(3):
+        g, dg = responses(xo)
+        xo_new = o.step(xo.copy(), g, dg)
+        g, dg = responses(xd.cpu().numpy())
+        mma_design_update(ops, xd, g, [dv.to_device(r) for r in dg], offset, xold1, xold2, 0.0, 1.0, 0.1, opt)
+        xold2, xold1 = xold1, xd.clone()
+        xd, xo = ops.x.clone(), xo_new
+        np.testing.assert_allclose(xd.cpu().numpy(), xo, rtol=0, atol=1e-7)
+    assert np.mean(np.abs(offset.cpu().numpy() / o.offset - 1.0) > 1e-9) < 0.01

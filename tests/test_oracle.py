@@ -189,3 +189,19 @@ def test_oc_oracle_against_golden():
         dx = flt.sensitivity(ds * 3 * (1 - 1e-9) * y ** 2)
         x = oc_update(x, dx)
     np.testing.assert_allclose(hist, g["history"][:4], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds"])
+def test_mma_oracle_against_golden(name):
+    """Oracle MMA update (numpy restatement of pymoto/common/mma.py) against pym.MMA.step on seeded subproblems."""
+    from make_golden_opt_inputs import subsolv_inputs
+    from oracle.nextrows import MMAOracle
+
+    g = load("mma_subsolv")
+    p = subsolv_inputs(name)
+    o = MMAOracle(p["n"], p["nresp"], move=p["move"], xmin=p["xmin"], xmax=p["xmax"], version=p["version"])
+    o.xold1, o.xold2 = p["xold1"].copy(), p["xold2"].copy()
+    xnew = o.step(p["x"].copy(), p["g"], p["dg"])
+    np.testing.assert_allclose(o.offset, g[name + "_offset"], rtol=1e-15)
+    np.testing.assert_allclose(o.low, g[name + "_low"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(xnew, g[name + "_xnew"], rtol=0, atol=1e-10)
