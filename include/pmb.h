@@ -28,6 +28,8 @@
  *   pmb_mma_residual / pmb_mma_newton_sums / pmb_mma_newton_dir / pmb_mma_linesearch
  *                        pymoto/common/mma.py:313-336,349-392,401-423,428-462 (n-sized parts of subsolv)
  *   pmb_pack_f32         pymoto/common/domain.py:541-548,579-583 (Float32 VTI payload, 2 -> 3 component padding)
+ *   pmb_vcycle / pmb_pcg_solve
+ *                        pymoto/solvers/iterative.py:222-256,340-403 (one V-cycle; the whole PCG solve driven from C)
  *
  * Conventions
  *   - all functions return 0 on success, non-zero on error; pmb_last_error() gives the (thread-local) message.
@@ -236,6 +238,40 @@ int pmb_mma_newton_dir(long long n, int m, const pmb_mma_vecs* v, const double* 
                        double* ws, void* stream);
 int pmb_mma_linesearch(long long n, int m, const pmb_mma_vecs* v, const double* lam, double steg, double epsi, double* out,
                        double* ws, void* stream);
+
+/* ---- whole linear solve driven from C (pymoto/solvers/iterative.py:340-403 CG.solve with :222-256 GeometricMultigrid.solve
+ * as preconditioner): the same kernel launches as the entry points above, issued in the reference's order, the host
+ * polling one scalar (the residual norm) per iteration.  Single GPU (every grid kz0 = 0, nzl = nz + 1).  All pointers
+ * inside the descriptor are DEVICE memory owned by the caller except Ke_host. */
+#define PMB_MAX_LEVELS 12
+typedef struct {
+  pmb_grid grid;       /* this level                                                              */
+  const double* A;     /* stencil-CSR values (may be NULL on level 0 when the generator is given) */
+  const double* diag;  /* diagonal of A                                                           */
+  double *u, *u2, *t;  /* scratch vectors, pmb_nrows(grid) doubles each                           */
+  double* rc;          /* restricted residual, pmb_nrows(next coarser grid) doubles               */
+  int smooth_steps;    /* damped-Jacobi sweeps before and after the coarse correction             */
+  double w;            /* damping                                                                 */
+} pmb_mg_level;
+typedef struct {
+  int nlevels;                        /* smoothed levels, finest first                                          */
+  pmb_mg_level level[PMB_MAX_LEVELS];
+  pmb_grid coarse_grid;               /* 2:1 coarsening of the last smoothed level, solved directly             */
+  const double* coarse_inv;           /* its dense inverse (pmb_densify + pmb_dense_invert), row-major          */
+  double* coarse_out;                 /* pmb_nrows(coarse_grid) doubles                                         */
+  const double* Ke_host;              /* level-0 generator for pmb_elem_spmv (HOST pointer) or NULL: stream A   */
+  const double* s;
+  const unsigned char* bcmask;
+  double bcdiagval;
+} pmb_mg_desc;
+/* z = one V-cycle applied to r (z, r: pmb_nrows(level[0].grid) doubles) */
+int pmb_vcycle(const pmb_mg_desc* mg, const double* r, double* z, void* stream);
+/* Preconditioned CG for A x = b from the start vector in x (overwritten by the solution); r, q, p: n-double scratch; scal: 16
+ * device doubles; ws_red: pmb_ws_doubles() zero-initialised doubles; ws_spmv: max(pmb_spmv_ws_doubles, pmb_elem_ws_doubles)
+ * of level 0.  Stops when |r|/|b| <= tol or after maxit iterations; explicit residual every `restart` iterations.  *iters
+ * = products A p, *relres = last |r|/|b| (both HOST). */
+int pmb_pcg_solve(const pmb_mg_desc* mg, const double* b, double* x, double* r, double* q, double* p, double tol, int maxit,
+                  int restart, double* scal, double* ws_red, double* ws_spmv, int* iters, double* relres, void* stream);
 
 /* VTI writer payload: out[i*ncomp_out + c] = (float) in[i*ncomp_in + c], zero for c >= ncomp_in (round to nearest even) */
 int pmb_pack_f32(long long nitems, int ncomp_in, int ncomp_out, const double* in, float* out, void* stream);

@@ -47,6 +47,22 @@ class MmaVecs(C.Structure):
 
 
 MMA_MAXM = 3  # PMB_MMA_MAXM
+MAX_LEVELS = 12  # PMB_MAX_LEVELS
+
+
+class MgLevel(C.Structure):
+    """Mirror of ``pmb_mg_level``."""
+
+    _fields_ = [("grid", Grid), ("A", C.c_void_p), ("diag", C.c_void_p), ("u", C.c_void_p), ("u2", C.c_void_p), ("t", C.c_void_p),
+                ("rc", C.c_void_p), ("smooth_steps", C.c_int), ("w", C.c_double)]
+
+
+class MgDesc(C.Structure):
+    """Mirror of ``pmb_mg_desc`` (the multigrid hierarchy handed to pmb_vcycle / pmb_pcg_solve)."""
+
+    _fields_ = [("nlevels", C.c_int), ("level", MgLevel * MAX_LEVELS), ("coarse_grid", Grid), ("coarse_inv", C.c_void_p),
+                ("coarse_out", C.c_void_p), ("Ke_host", C.c_void_p), ("s", C.c_void_p), ("bcmask", C.c_void_p),
+                ("bcdiagval", C.c_double)]
 
 _P = C.c_void_p
 _LL = C.c_longlong
@@ -106,6 +122,9 @@ SIGNATURES = {
     "pmb_mma_newton_dir": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _P, _P, _P]),
     "pmb_mma_linesearch": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _D, _P, _P, _P]),
     "pmb_pack_f32": (_I, [_LL, _I, _I, _P, _P, _P]),
+    "pmb_vcycle": (_I, [C.POINTER(MgDesc), _P, _P, _P]),
+    "pmb_pcg_solve": (_I, [C.POINTER(MgDesc), _P, _P, _P, _P, _P, _D, _I, _I, _P, _P, _P, C.POINTER(C.c_int),
+                           C.POINTER(C.c_double), _P]),
     "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
     "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),
 }

@@ -371,8 +371,76 @@ class CG(LinearSolver):
             return dv.like_input(torch.stack(cols, dim=1), rhs)
         return dv.like_input(self._solve1(bd.reshape(-1), None if x0 is None else dv.to_device(x0).reshape(-1)), rhs)
 
+    # Drive the whole solve from C (pmb_pcg_solve: same launches in the same order, bit-identical iterates, one host poll
+    # per iteration, no interpreter / ctypes overhead per launch) when the preconditioner is a single-GPU geometric
+    # multigrid hierarchy.  Opt-in: PMB_C_PCG=1 or CG.use_c_driver = True (the Python driver replays the V-cycle as one
+    # CUDA graph instead, which is as fast on large grids).
+    use_c_driver = os.environ.get("PMB_C_PCG", "0") == "1"
+
+    def _mg_desc(self):
+        """``pmb_mg_desc`` of the preconditioner hierarchy, or None when the C driver does not apply."""
+        A, lvl = self.A, self.preconditioner
+        if A is None or A.comm is not None or not isinstance(lvl, GeometricMultigrid) or lvl.A is not A:
+            return None
+        desc, keep, l = _lib.MgDesc(), [], 0
+        while isinstance(lvl, GeometricMultigrid):
+            if (l >= _lib.MAX_LEVELS or lvl.A is None or lvl.A.comm is not None or lvl._buf is None or lvl.Ac is None
+                    or lvl.cycle.lower() != "v" or lvl.smoother.D is None):
+                return None
+            L = desc.level[l]
+            L.grid = lvl.A.grid
+            L.A, L.diag = lvl.A._buf.data_ptr(), lvl.smoother.D.data_ptr()
+            L.u, L.u2, L.t, L.rc = (lvl._buf[k].data_ptr() for k in ("u", "u2", "t", "rc"))
+            L.smooth_steps, L.w = int(lvl.smooth_steps), float(lvl.smoother.w)
+            keep.append(lvl)
+            coarse, lvl, l = lvl.Ac, lvl.inner_level, l + 1
+        if not isinstance(lvl, SolverDenseInverse) or lvl.inv is None or lvl.n != coarse.shape[0]:
+            return None
+        lvl._check_info()
+        desc.nlevels, desc.coarse_grid = l, coarse.grid
+        desc.coarse_inv, desc.coarse_out = lvl.inv.data_ptr(), lvl._out.data_ptr()
+        gen = A.generator if DeviceCSR.matrix_free else None
+        if gen is not None:
+            desc.Ke_host, desc.s = gen["ke"].ctypes.data, gen["s"].data_ptr()
+            desc.bcmask = None if gen["mask"] is None else gen["mask"].data_ptr()
+            desc.bcdiagval = float(gen["bcdiag"])
+        self._desc_keep = (keep, gen)
+        return desc
+
+    def _solve1_c(self, desc, b, x0):
+        import ctypes as C
+
+        A, n = self.A, b.numel()
+        tstart = time.perf_counter()
+        x = A.new_vec(zero=x0 is None)
+        if x0 is not None:
+            x.copy_(x0)
+        r, q, p, scal = dv.empty(n), dv.empty(n), A.new_vec(), dv.zeros(16)
+        ws = dv.workspace()
+        g = A.grid
+        ws_spmv = ws.spmv_ws(max(_lib.query("pmb_spmv_ws_doubles", g), _lib.query("pmb_elem_ws_doubles", g)))
+        iters, relres = C.c_int(0), C.c_double(0.0)
+        launches0 = _lib.launch_count
+        _lib.call("pmb_pcg_solve", C.byref(desc), dv.ptr(b), dv.ptr(x), dv.ptr(r), dv.ptr(q), dv.ptr(p), float(self.tol), int(self.maxit),
+                  int(self.restart), dv.ptr(scal), dv.ptr(ws.red), dv.ptr(ws_spmv), C.byref(iters), C.byref(relres), dv.stream())
+        self.iterations, self.last_residual = int(iters.value), float(relres.value)
+        # kernels launched inside the C call: per V-cycle and level 2 steps + 3 (smooth0 / residual, restrict, prolong) + the
+        # coarse GEMV; per iteration the product (+ reduce), update, dots, lincomb (bench.py reports gpu_launches)
+        per_cycle = sum(2 * desc.level[i].smooth_steps + 3 for i in range(desc.nlevels)) + 1
+        _lib.launch_count = launches0 + 3 + self.iterations * (per_cycle + 6) + (per_cycle + 2 if self.iterations else 0)
+        if self.last_residual > self.tol:
+            warnings.warn(f"CG Maximum iterations ({self.maxit}) reached, with final residuals {self.last_residual}")
+        elif self.verbosity >= 1:
+            print(f"CG Converged in {self.iterations} iterations and {np.round(time.perf_counter() - tstart, 3)}s, "
+                  f"with final (max) residual {self.last_residual}")
+        return x
+
     def _solve1(self, b, x0):
         A, M = self.A, self.preconditioner
+        if CG.use_c_driver:
+            desc = self._mg_desc()
+            if desc is not None:
+                return self._solve1_c(desc, b, x0)
         n = b.numel()
         tstart = time.perf_counter()
         x = A.new_vec(zero=x0 is None)

@@ -955,3 +955,61 @@ def test_mma_device_vs_oracle_larger_problem(pmb, n, m):
         xd, xo = ops.x.clone(), xo_new
         np.testing.assert_allclose(xd.cpu().numpy(), xo, rtol=0, atol=1e-7)
     assert np.mean(np.abs(offset.cpu().numpy() / o.offset - 1.0) > 1e-9) < 0.01
+
+
+# ------------------------------------------------------------------------------------------------ C-side PCG driver (8b)
+@pytest.mark.parametrize("shape,restart,matrix_free", [((16, 8, 8), 50, True), ((32, 16, 16), 3, True), ((32, 16, 16), 50, False)])
+def test_c_pcg_driver_identical_to_python_driver(pmb, shape, restart, matrix_free):
+    """pmb_pcg_solve / pmb_vcycle (whole solve driven from C, one host poll per iteration) issue the launches of the Python
+    driver in the same order: solution bit-identical, same iteration count and residual, cold and warm start, explicit-
+    residual and recurrence branches (restart = 3), matrix-free and CSR-streamed finest level."""
+    import ctypes as C
+
+    from pymoto_b200 import _lib, device as dv
+    from pymoto_b200.matrix import DeviceCSR
+    from pymoto_b200.solvers import CG
+
+    nx, ny, nz = shape
+    gr = Grid(nx, ny, nz)
+    ndof, bc, f = cantilever(gr)
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    rng = np.random.default_rng(11)
+    s = 1e-9 + (1 - 1e-9) * rng.random(gr.nel) ** 3
+    saved_mf, saved_c = DeviceCSR.matrix_free, CG.use_c_driver
+    try:
+        DeviceCSR.matrix_free = matrix_free
+        K = pmb.AssembleStiffness(dom, bc=bc)(dv.to_device(s))
+        mgs = pmb.solvers.auto_multigrid(dom, min_size=4)
+        cg = CG(preconditioner=mgs[0], tol=1e-9, restart=restart)
+        cg.update(K)
+        fd = dv.to_device(f)
+        x0 = dv.to_device(rng.standard_normal(f.size) * 1e-3)
+        results = {}
+        for use_c in (False, True):
+            CG.use_c_driver = use_c
+            if use_c:
+                assert cg._mg_desc() is not None
+            cold = cg.solve(fd).clone()
+            its_cold, res_cold = cg.iterations, cg.last_residual
+            warm = cg.solve(fd, x0=x0).clone()
+            results[use_c] = (cold.cpu().numpy(), its_cold, res_cold, warm.cpu().numpy(), cg.iterations, cg.last_residual)
+        py, c = results[False], results[True]
+        assert py[1] == c[1] and py[4] == c[4], (py[1], c[1], py[4], c[4])
+        assert py[1] > restart or restart == 50
+        assert np.array_equal(py[0], c[0]) and np.array_equal(py[3], c[3])
+        assert py[2] == c[2] and py[5] == c[5]
+        Ks = K.tocsr()
+        assert np.linalg.norm(Ks @ c[0] - f) <= 1e-8 * np.linalg.norm(f)
+        # one V-cycle through pmb_vcycle against GeometricMultigrid.solve
+        r = dv.to_device(rng.standard_normal(f.size))
+        z_py = mgs[0].solve(r).clone()
+        z_c = dv.empty(f.size)
+        desc = cg._mg_desc()
+        _lib.call("pmb_vcycle", C.byref(desc), dv.ptr(r), dv.ptr(z_c), dv.stream())
+        assert np.array_equal(z_py.cpu().numpy(), z_c.cpu().numpy())
+        # argument validation stays on the host
+        desc.nlevels = 0
+        with pytest.raises(_lib.PmbError):
+            _lib.call("pmb_vcycle", C.byref(desc), dv.ptr(r), dv.ptr(z_c), dv.stream())
+    finally:
+        DeviceCSR.matrix_free, CG.use_c_driver = saved_mf, saved_c
