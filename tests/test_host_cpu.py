@@ -195,3 +195,40 @@ def test_filterconv_axis_maps_match_reference_padding():
     for bc0, bc1 in [("symmetric", "edge"), ("edge", "wrap"), ("wrap", "symmetric"), ("wrap", "wrap"), ("edge", "edge")]:
         ref = pym.FilterConv(d, weights=np.ones((5, 1, 1)), xmin_bc=bc0, xmax_bc=bc1)
         assert ref.el3d_pad[:, 0, 0].tolist() == FilterConv._axis_map(7, 2, bc0, bc1)[0].tolist(), (bc0, bc1)
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct in include/pmb.h as the C compiler lays it out vs the ctypes mirrors in
+    pymoto_b200/_lib.py (a silent mismatch would corrupt arguments passed by value or by pointer)."""
+    import subprocess
+
+    from pymoto_b200 import _lib
+
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "pmb.h"
+#define S(t) printf(#t " %zu\n", sizeof(t))
+#define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
+int main(void) {
+  S(pmb_grid); S(pmb_coef); S(pmb_bound); S(pmb_mma_vecs); S(pmb_mg_level); S(pmb_mg_desc);
+  O(pmb_coef, sqrt_den); O(pmb_bound, v); O(pmb_mma_vecs, Q); O(pmb_mg_level, A); O(pmb_mg_level, smooth_steps);
+  O(pmb_mg_level, w); O(pmb_mg_desc, level); O(pmb_mg_desc, coarse_grid); O(pmb_mg_desc, coarse_inv); O(pmb_mg_desc, Ke_host);
+  O(pmb_mg_desc, bcdiagval);
+  printf("PMB_MMA_MAXM %d\nPMB_MAX_LEVELS %d\n", PMB_MMA_MAXM, PMB_MAX_LEVELS);
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    mirrors = {"pmb_grid": _lib.Grid, "pmb_coef": _lib.Coef, "pmb_bound": _lib.Bound, "pmb_mma_vecs": _lib.MmaVecs,
+               "pmb_mg_level": _lib.MgLevel, "pmb_mg_desc": _lib.MgDesc}
+    for name, cls in mirrors.items():
+        assert int(got[name]) == ctypes.sizeof(cls), (name, got[name], ctypes.sizeof(cls))
+    for key, val in got.items():
+        if "." in key:
+            st, field = key.split(".")
+            assert int(val) == getattr(mirrors[st], field).offset, (key, val)
+    assert int(got["PMB_MMA_MAXM"]) == _lib.MMA_MAXM and int(got["PMB_MAX_LEVELS"]) == _lib.MAX_LEVELS
