@@ -117,7 +117,7 @@ long long pmb_elem_ws_doubles(const pmb_grid* g);
  * layout for ndof = 3, y equal to rounding).  set pins the layout for this process, get reads the one used for `ndof` dofs per node (initially PMB_ELEM_VARIANT or
  * 0);
  * pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's operands, stores the launch times in
- * ms_out[pmb_elem_num_variants()] and keeps the fastest for that ndof.  Not capturable into a CUDA graph. */
+ * ms_out[pmb_elem_num_variants()] and keeps the fastest of the bit-identical layouts (0..2) for that ndof.  Not capturable into a CUDA graph. */
 int pmb_elem_set_variant(int variant);
 int pmb_elem_get_variant(int ndof);
 int pmb_elem_num_variants(void);
