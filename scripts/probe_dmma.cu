@@ -1,3 +1,8 @@
+// Probe: FP64 tensor-core (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4) vs DFMA throughput on one GPU, 4..32 resident warps per SM,
+// 8 independent accumulator fragments per warp.  Build and run on the GPU box:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 scripts/probe_dmma.cu -o /tmp/probe_dmma && /tmp/probe_dmma
+// Result on the round-1 B200 (profiles/probe_dmma_r1.txt): DMMA 37.1-37.2 TFLOP/s, DFMA 32.7-34.2 TFLOP/s -- the FP64 tensor
+// path has the same peak as the vector path but needs 8x fewer issue slots (basis of elem_kernel_mma, pmb_elem.cu).
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
