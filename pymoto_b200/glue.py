@@ -6,8 +6,6 @@ kernels / the deterministic device reduction); like every module of this package
 tensors and return the kind they were given, so a design iteration can stay resident in HBM between the filter, the
 assembly and the solve.  (The reference's own MathExpression / EinSum remain usable on numpy Signals next to them.)
 """
-import numpy as np
-
 from . import _lib
 from . import device as dv
 from .core import Module

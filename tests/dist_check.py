@@ -27,7 +27,7 @@ def main():
         ge.build()
     dist.barrier()
     import pymoto_b200 as pmb
-    from pymoto_b200 import device as dv, _lib
+    from pymoto_b200 import device as dv
     from oracle import Grid
     from oracle.chain import ComplianceProblem
 
