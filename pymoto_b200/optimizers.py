@@ -14,9 +14,20 @@ from . import _lib
 from . import device as dv
 
 
+def _require_single_rank(who):
+    """The design updates reduce over the design vector of THIS rank only (volume, Newton sums, step lengths): with a slab
+    decomposition every rank would take a different step.  Refuse instead of returning a wrong design."""
+    from . import slab
+
+    if slab.context().active:
+        raise NotImplementedError(f"pymoto_b200.{who}: the design update is not distributed over z-slabs yet "
+                                  "(its reductions are rank-local); gather the design on one rank or use one GPU")
+
+
 class OC:
     def __init__(self, variables, response, function, move=0.1, xmin=0.0, xmax=1.0, verbosity: int = 2, l1init: float = 0.0,
                  l2init: float = 100000.0, l1l2tol: float = 1e-4, maxvol: float = None):
+        _require_single_rank("OC")
         if isinstance(variables, (list, tuple)):
             if len(variables) != 1:
                 raise NotImplementedError("pymoto_b200.OC handles one design-variable Signal")
@@ -271,6 +282,7 @@ class MMA:
     def __init__(self, variables, responses, function, slice_network=False, move=0.1, xmin=0.0, xmax=1.0, verbosity=2,
                  mmaversion="MMA2007", **kwargs):
         dv.require_cuda()
+        _require_single_rank("MMA")
         if slice_network:
             raise NotImplementedError("pymoto_b200.MMA evaluates the whole Network (slice_network=False)")
         self.variables = list(variables) if isinstance(variables, (list, tuple)) else [variables]
