@@ -13,6 +13,7 @@
  *   pmb_restrict         pymoto/solvers/iterative.py:244      (R^T r, csc_matvec)
  *   pmb_prolong_add      pymoto/solvers/iterative.py:250      (u += R u_c, csr_matvec)
  *   pmb_galerkin         pymoto/solvers/iterative.py:173      (R^T A R, csr_matmat x2)
+ *   pmb_galerkin_direct  the same call site on level 0, evaluated from x_e and Ke (+ pmb_scatter_add for the bc term)
  *   pmb_densify / pmb_dense_invert / pmb_dense_gemv
  *                        pymoto/solvers/sparse.py:533-550     (splu + solve on the coarsest operator)
  *   pmb_dots / pmb_lincomb / pmb_cg_xr_update
@@ -106,24 +107,46 @@ long long pmb_ws_doubles(void);
 
 /* Matrix-free application of the FINEST-level operator K = P (sum_e s_e Ke) P + bcdiagval (I - P) from the element
  * scaling vector s (the x that pmb_assemble was given: points at element layer kz0, layer kz0-1 read as halo) instead
- * of the assembled values.  Same modes, epilogues and fused dot products as pmb_spmv.  Ke is a HOST pointer (it is
- * passed to the kernel through the parameter constant bank).  ws: pmb_elem_ws_doubles(g) doubles. */
-int pmb_elem_spmv(const pmb_grid* g, int mode, const double* Ke_host, const double* s, const unsigned char* bcmask,
-                  double bcdiagval, const double* x, const double* b, const double* diag, double w, double* y,
-                  const double* dotv, double* dot_out, double* ws, void* stream);
+ * of the assembled values.  Same modes, epilogues and fused dot products as pmb_spmv.  The operator is described by a
+ * caller-owned POD (no state is kept in the library):
+ *   Ke_host     (nn*ndof)^2 row-major, HOST pointer (passed to the kernel through the parameter constant bank)
+ *   s, bcmask   DEVICE pointers (bcmask: 1 byte per dof, may be NULL); bcdiagval: diagonal of the Dirichlet rows
+ *   brickflags  optional DEVICE bytes from pmb_elem_brickflags (layouts 4 - 6 skip all Dirichlet-mask traffic in bricks whose
+ *               flag is 0; NULL = every brick checks the mask)
+ *   variant     kernel layout, 0 .. pmb_elem_num_variants()-1 (3-D, ndof 1 or 3; everything else runs layout 0):
+ *               0 = one node per thread on a 32x4x2 brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered
+ *               planes, 3 = FP64 tensor-core (DMMA) layout for ndof = 3 (y equal to rounding), 4 / 5 = persistent CTAs
+ *               (3 / 2 per SM) whose bricks are staged by TMA bulk copies into a 2-stage ring, 6 = FP64 tensor-core layout
+ *               marching along y with in-register accumulation (ndof = 3, y equal to rounding).  Layouts 0, 1, 2, 4, 5
+ *               give bit-identical y.
+ * Layouts 4 - 6 copy whole 16-byte granules: the granules holding the first / last element of x and s must be readable
+ * (true for any cudaMalloc'ed array; vectors from DeviceCSR.new_vec() are plane-padded).
+ * ws: pmb_elem_ws_doubles(g) doubles. */
+typedef struct {
+  const double* Ke_host;
+  const double* s;
+  const unsigned char* bcmask;
+  double bcdiagval;
+  const unsigned char* brickflags;
+  int variant;
+} pmb_elem_op;
+int pmb_elem_spmv(const pmb_grid* g, int mode, const pmb_elem_op* op, const double* x, const double* b, const double* diag,
+                  double w, double* y, const double* dotv, double* dot_out, double* ws, void* stream);
 long long pmb_elem_ws_doubles(const pmb_grid* g);
-/* The 3-D kernel behind pmb_elem_spmv exists in pmb_elem_num_variants() layouts (0 = one node per thread on a 32x4x2
- * brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered planes, bit-identical y; 3 = FP64 tensor-core (DMMA)
- * layout for ndof = 3, y equal to rounding).  set pins the layout for this process, get reads the one used for `ndof` dofs per node (initially PMB_ELEM_VARIANT or
- * 0);
- * pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's operands, stores the launch times in
- * ms_out[pmb_elem_num_variants()] and keeps the fastest of the bit-identical layouts (0..2) for that ndof.  Not capturable into a CUDA graph. */
-int pmb_elem_set_variant(int variant);
-int pmb_elem_get_variant(int ndof);
 int pmb_elem_num_variants(void);
-int pmb_elem_autotune(const pmb_grid* g, const double* Ke_host, const double* s, const unsigned char* bcmask,
-                      double bcdiagval, const double* x, const double* b, const double* diag, double* y,
-                      double* ms_out, void* stream);
+/* flags[unit] = 1 iff the region of the slab that layout `variant` (4, 5: a 32x4x2-node brick + 1-node apron; 6: one
+ * 8-row step of a 32x2 node-column strip) stages for that unit of work holds a masked dof; pmb_elem_brickflags_bytes(g,
+ * variant) bytes.  Computed once per bc set, slab and layout. */
+long long pmb_elem_brickflags_bytes(const pmb_grid* g, int variant);
+int pmb_elem_brickflags(const pmb_grid* g, int variant, const unsigned char* bcmask, unsigned char* flags, void* stream);
+/* pmb_elem_autotune times every layout (Jacobi mode, y is scratch) on the caller's operands, stores the launch times in
+ * ms_out[pmb_elem_num_variants()] and the fastest admissible layout in *best (the caller writes it into its pmb_elem_op):
+ * allow_rounding = 0 admits only the layouts bit-identical to layout 0, != 0 also the tensor-core layouts (3, 6).
+ * flags_scratch: pmb_elem_autotune_flag_bytes(g) bytes (brick flags are layout-specific and recomputed per layout; may be
+ * NULL when op->bcmask is NULL).  Not capturable into a CUDA graph. */
+long long pmb_elem_autotune_flag_bytes(const pmb_grid* g);
+int pmb_elem_autotune(const pmb_grid* g, const pmb_elem_op* op, const double* x, const double* b, const double* diag, double* y,
+                      unsigned char* flags_scratch, int allow_rounding, double* ms_out, int* best, void* stream);
 
 /* u = w * (r / diag) */
 int pmb_smooth0(long long n, double w, const double* r, const double* diag, double* u, void* stream);
@@ -140,6 +163,17 @@ long long pmb_galerkin_ws_doubles(const pmb_grid* gf);
  * rows = row collapse Ac = R^T B of the owned coarse rows */
 int pmb_galerkin_cols(const pmb_grid* gf, const pmb_grid* gc, const double* Af, double* work, void* stream);
 int pmb_galerkin_rows(const pmb_grid* gf, const pmb_grid* gc, const double* work, double* Ac, void* stream);
+
+/* K6 (direct): the level-1 operator straight from the element scaling vector of the finest level, Ac = sum_E sum_p
+ * s_child(E,p) G_id(E,p) -- the fine matrix is never read (derivation and host set-up: pymoto_b200/coarse.py; replaces the two
+ * csr_matmat of pymoto/solvers/iterative.py:173 on level 0).  Gtab: ntab tables of 8 x 8 x ndof x ndof doubles ([a][b][d][c];
+ * entries 0..7 = unmasked children, the rest = children touching Dirichlet dofs); cidx (may be NULL): int32 per GLOBAL
+ * coarse element, -1 or the row of child_ids (8 uint16 table indices per such element).  s as for pmb_assemble, but TWO
+ * halo layers below the fine slab are read.  The Dirichlet diagonal term bcdiagval R^T (I-P) R is added afterwards by
+ * pmb_scatter_add(n, idx, val, data): data[idx[i]] += val[i], idx unique. */
+int pmb_galerkin_direct(const pmb_grid* gf, const pmb_grid* gc, const double* Gtab, const int* cidx, const unsigned short* child_ids,
+                        const double* s, double* Ac, void* stream);
+int pmb_scatter_add(long long n, const long long* idx, const double* val, double* data, void* stream);
 
 /* K7: coarsest level. dense is n*n row-major. pmb_dense_invert inverts in place (blocked Gauss-Jordan without
  * pivoting, valid for SPD); scratch holds pmb_dense_invert_ws_doubles(n) doubles; info (device int) is set non-zero
@@ -242,7 +276,7 @@ int pmb_mma_linesearch(long long n, int m, const pmb_mma_vecs* v, const double* 
 /* ---- whole linear solve driven from C (pymoto/solvers/iterative.py:340-403 CG.solve with :222-256 GeometricMultigrid.solve
  * as preconditioner): the same kernel launches as the entry points above, issued in the reference's order, the host
  * polling one scalar (the residual norm) per iteration.  Single GPU (every grid kz0 = 0, nzl = nz + 1).  All pointers
- * inside the descriptor are DEVICE memory owned by the caller except Ke_host. */
+ * inside the descriptor are DEVICE memory owned by the caller except gen.Ke_host. */
 #define PMB_MAX_LEVELS 12
 typedef struct {
   pmb_grid grid;       /* this level                                                              */
@@ -259,10 +293,7 @@ typedef struct {
   pmb_grid coarse_grid;               /* 2:1 coarsening of the last smoothed level, solved directly             */
   const double* coarse_inv;           /* its dense inverse (pmb_densify + pmb_dense_invert), row-major          */
   double* coarse_out;                 /* pmb_nrows(coarse_grid) doubles                                         */
-  const double* Ke_host;              /* level-0 generator for pmb_elem_spmv (HOST pointer) or NULL: stream A   */
-  const double* s;
-  const unsigned char* bcmask;
-  double bcdiagval;
+  pmb_elem_op gen;                    /* level-0 generator for pmb_elem_spmv; gen.Ke_host == NULL: stream A      */
 } pmb_mg_desc;
 /* z = one V-cycle applied to r (z, r: pmb_nrows(level[0].grid) doubles) */
 int pmb_vcycle(const pmb_mg_desc* mg, const double* r, double* z, void* stream);
@@ -272,6 +303,11 @@ int pmb_vcycle(const pmb_mg_desc* mg, const double* r, double* z, void* stream);
  * = products A p, *relres = last |r|/|b| (both HOST). */
 int pmb_pcg_solve(const pmb_mg_desc* mg, const double* b, double* x, double* r, double* q, double* p, double tol, int maxit,
                   int restart, double* scal, double* ws_red, double* ws_spmv, int* iters, double* relres, void* stream);
+
+/* In-run FP64 peak probe for bench.py's roofline (not on the product path): kind 0 = DFMA, 1 = DMMA.8x8x4 register-only
+ * streams at 16 warps / SM; *tflops_out (HOST) = best of 3 launches; out: pmb_probe_fp64_out_doubles() device doubles. */
+long long pmb_probe_fp64_out_doubles(void);
+int pmb_probe_fp64(int kind, int iters, double* out, double* tflops_out, void* stream);
 
 /* VTI writer payload: out[i*ncomp_out + c] = (float) in[i*ncomp_in + c], zero for c >= ncomp_in (round to nearest even) */
 int pmb_pack_f32(long long nitems, int ncomp_in, int ncomp_out, const double* in, float* out, void* stream);

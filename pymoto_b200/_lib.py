@@ -46,6 +46,13 @@ class MmaVecs(C.Structure):
     _fields_ = [(nm, C.c_void_p) for nm in NAMES]
 
 
+class ElemOp(C.Structure):
+    """Mirror of ``pmb_elem_op``: the matrix-free finest-level operator (host Ke, device s / mask / brick flags, kernel layout)."""
+
+    _fields_ = [("Ke_host", C.c_void_p), ("s", C.c_void_p), ("bcmask", C.c_void_p), ("bcdiagval", C.c_double),
+                ("brickflags", C.c_void_p), ("variant", C.c_int)]
+
+
 MMA_MAXM = 3  # PMB_MMA_MAXM
 MAX_LEVELS = 12  # PMB_MAX_LEVELS
 
@@ -61,8 +68,7 @@ class MgDesc(C.Structure):
     """Mirror of ``pmb_mg_desc`` (the multigrid hierarchy handed to pmb_vcycle / pmb_pcg_solve)."""
 
     _fields_ = [("nlevels", C.c_int), ("level", MgLevel * MAX_LEVELS), ("coarse_grid", Grid), ("coarse_inv", C.c_void_p),
-                ("coarse_out", C.c_void_p), ("Ke_host", C.c_void_p), ("s", C.c_void_p), ("bcmask", C.c_void_p),
-                ("bcdiagval", C.c_double)]
+                ("coarse_out", C.c_void_p), ("gen", ElemOp)]
 
 _P = C.c_void_p
 _LL = C.c_longlong
@@ -82,12 +88,13 @@ SIGNATURES = {
     "pmb_rowstats": (_I, [_G, _P, _P, _P, _P]),
     "pmb_spmv": (_I, [_G, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "pmb_spmv_ws_doubles": (_LL, [_G]),
-    "pmb_elem_spmv": (_I, [_G, _I, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
+    "pmb_elem_spmv": (_I, [_G, _I, C.POINTER(ElemOp), _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "pmb_elem_ws_doubles": (_LL, [_G]),
-    "pmb_elem_set_variant": (_I, [_I]),
-    "pmb_elem_get_variant": (_I, [_I]),
     "pmb_elem_num_variants": (_I, []),
-    "pmb_elem_autotune": (_I, [_G, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P]),
+    "pmb_elem_brickflags_bytes": (_LL, [_G, _I]),
+    "pmb_elem_brickflags": (_I, [_G, _I, _P, _P, _P]),
+    "pmb_elem_autotune_flag_bytes": (_LL, [_G]),
+    "pmb_elem_autotune": (_I, [_G, C.POINTER(ElemOp), _P, _P, _P, _P, _P, _I, _P, C.POINTER(C.c_int), _P]),
     "pmb_ws_doubles": (_LL, []),
     "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
     "pmb_restrict": (_I, [_G, _G, _P, _P, _P]),
@@ -96,6 +103,8 @@ SIGNATURES = {
     "pmb_galerkin_ws_doubles": (_LL, [_G]),
     "pmb_galerkin_cols": (_I, [_G, _G, _P, _P, _P]),
     "pmb_galerkin_rows": (_I, [_G, _G, _P, _P, _P]),
+    "pmb_galerkin_direct": (_I, [_G, _G, _P, _P, _P, _P, _P, _P]),
+    "pmb_scatter_add": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_densify": (_I, [_G, _P, _P, _P]),
     "pmb_dense_invert": (_I, [_I, _P, _P, _P, _P]),
     "pmb_dense_invert_ws_doubles": (_LL, [_I]),
@@ -121,6 +130,8 @@ SIGNATURES = {
     "pmb_mma_newton_sums": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _P, _P, _P]),
     "pmb_mma_newton_dir": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _P, _P, _P]),
     "pmb_mma_linesearch": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _D, _P, _P, _P]),
+    "pmb_probe_fp64_out_doubles": (_LL, []),
+    "pmb_probe_fp64": (_I, [_I, _I, _P, C.POINTER(C.c_double), _P]),
     "pmb_pack_f32": (_I, [_LL, _I, _I, _P, _P, _P]),
     "pmb_vcycle": (_I, [C.POINTER(MgDesc), _P, _P, _P]),
     "pmb_pcg_solve": (_I, [C.POINTER(MgDesc), _P, _P, _P, _P, _P, _D, _I, _I, _P, _P, _P, C.POINTER(C.c_int),
@@ -141,9 +152,11 @@ def _kernels_launched(name, args):
     if name == "pmb_spmv":
         return 2 if args[9] is not None else 1  # + reduce_triples_kernel when the fused dots are requested
     if name == "pmb_elem_spmv":
-        return 2 if args[12] is not None else 1
+        return 2 if args[9] is not None else 1
     if name == "pmb_elem_autotune":
         return 8 * load().pmb_elem_num_variants()  # every variant: 2 warm-up + 6 timed launches
+    if name == "pmb_probe_fp64":
+        return 4
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":
@@ -171,10 +184,24 @@ def load():
 profile_times = None  # set to {} to time every call with CUDA events (synchronising; diagnostics only)
 
 
+def _stat_key(name, args):
+    """(entry point, detail): detail = (nx, mode) for the operator kernels, (nx, None) for other grid-first calls, (n, None)
+    for vector calls -- enough for bench.py to attribute launches and algorithmic bytes to multigrid levels."""
+    a0 = args[0] if args else None
+    if name in ("pmb_spmv", "pmb_elem_spmv"):
+        return (name, (a0.nx, args[1]))
+    if isinstance(a0, Grid):
+        return (name, (a0.nx, None))
+    if isinstance(a0, int):
+        return (name, (a0, None))
+    return (name, None)
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise PmbError with pmb_last_error() on failure."""
     global launch_count
     lib = load()
+    key = _stat_key(name, args)
     if profile_times is not None:
         import torch
 
@@ -183,14 +210,12 @@ def call(name, *args):
         rc = getattr(lib, name)(*args)
         e1.record()
         e1.synchronize()
-        key = (name, (args[0].nx, args[1])) if name in ("pmb_spmv", "pmb_elem_spmv") else (name, args[0].nx if isinstance(args[0], Grid) else None)
         t = profile_times.setdefault(key, [0, 0.0])
         t[0] += 1
         t[1] += e0.elapsed_time(e1)
     else:
         rc = getattr(lib, name)(*args)
     launch_count += _kernels_launched(name, args)
-    key = (name, (args[0].nx, args[1])) if name in ("pmb_spmv", "pmb_elem_spmv") else (name, None)
     call_stats[key] = call_stats.get(key, 0) + 1
     if rc != 0:
         raise PmbError(f"{name} failed: {lib.pmb_last_error().decode()}")

@@ -13,7 +13,7 @@ from . import device as dv
 from .core import Module
 from .domain import grid_dims
 from .dyad import DeviceDyad
-from .matrix import DeviceCSR, make_grid
+from .matrix import DeviceCSR, ElemGenerator, make_grid
 from . import slab
 
 
@@ -135,12 +135,13 @@ class AssembleGeneral(Module):
         x = dv.to_device(xscale).reshape(-1)
         # private copy of the scaling vector (it also generates the matrix-free finest-level operator until the next
         # call) with room for the element layer below my first node plane, fetched from the rank below
+        # (two layers: the direct level-1 Galerkin build reads the children of the coarse element layer below the slab)
         if self._xbuf is None:
-            self._xbuf = dv.zeros(self.nel + self._lay)
-        self._xbuf[self._lay:] = x
+            self._xbuf = dv.zeros(self.nel + 2 * self._lay)
+        self._xbuf[2 * self._lay:] = x
         if self._ctx.active:
-            self._ctx.comm.exchange(self._xbuf, self._lay, self.nel, self._lay, lower=True, upper=False)
-        x = self._xbuf[self._lay:]
+            self._ctx.comm.exchange(self._xbuf, 2 * self._lay, self.nel, self._lay, lower=True, upper=False, width=2)
+        x = self._xbuf[2 * self._lay:]
         # a fresh value buffer each call would cost 8*nnz bytes of allocation per design iteration; the matrix
         # object is reused and its cached row statistics dropped (consumers re-read it on every update()).
         if self._mat is None:
@@ -149,8 +150,11 @@ class AssembleGeneral(Module):
         _lib.call("pmb_assemble", self.grid, self._Ke_host.ctypes.data, dv.ptr(x), dv.ptr(self._bcmask),
                   float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
         mat.invalidate()
-        mat.generator = dict(ke=self._Ke_host, s=x, mask=self._bcmask,
-                             bcdiag=float(self.bcdiagval if self.bcdiagval is not None else 0.0))
+        if mat.generator is None:
+            mat.generator = ElemGenerator(self.grid, self._Ke_host, x, self._bcmask,
+                                          float(self.bcdiagval if self.bcdiagval is not None else 0.0), bc=self.bc)
+        else:
+            mat.generator.retarget(x)
         mat.autotune_matrix_free()
         return mat
 

@@ -656,6 +656,671 @@ __global__ void __launch_bounds__(MM_NT, 2)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Ring layout (variant 4, 3-D): persistent CTAs, bricks staged by TMA bulk copies into a 2-stage shared-memory ring.
+//
+// Source-level sampling of elem_kernel put 58 % of a warp's lifetime into the staging prologue (per-thread index
+// arithmetic, predicates, __ldg latency before the barrier) while the FMA phase itself runs at the FP64 pipe rate.  Here
+// the staging leaves the instruction stream: a CTA walks its bricks round-robin, and while brick t is in its FMA phase the
+// 24 x-rows (34 nodes each) and 15 density rows of brick t+1 are already in flight as 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx::bytes; SASS UBLKCP), one row per lane of warp 0, landing in the other ring
+// stage.  A tensor-map (cp.async.bulk.tensor) cannot describe the planes: its global strides must be multiples of 16 bytes
+// and a node row is NX*NDOF doubles (771 for 257 nodes x 3 dofs), so every row is copied from its own 16-byte-aligned hull
+// and read back with a per-row shift of 0 or 1 double.  Nothing is zero-filled or masked on the way in:
+//   * out-of-grid node slots keep finite stale values and are only ever multiplied by the density of an out-of-grid
+//     element, which IS forced to +0.0 (edge bricks patch their density tile after the copies land);
+//   * Dirichlet columns are zeroed in shared memory only in bricks whose staged region holds a constrained dof
+//     (`brickflags`, one byte per brick from pmb_elem_brickflags; bc sets are fixed over a design run).
+// Per element the (dk, dj, di) FMA order of elem_kernel is kept, so y is bit-identical to variants 0-2.
+// ---------------------------------------------------------------------------------------------------------
+template <int NDOF>
+struct RingCfg {
+  static constexpr int BX = 32, BY = 4, BZ = 2, NT = BX * BY * BZ;
+  static constexpr int TX = BX + 2, TY = BY + 2, TZ = BZ + 2, SZ = BZ + 1;
+  static constexpr int XROWS = TZ * TY, XLEN = TX * NDOF, XPITCH = (XLEN + 2 + 1) / 2 * 2;
+  static constexpr int SROWS = SZ * (BY + 1), SLEN = BX + 1, SPITCH = (SLEN + 2 + 1) / 2 * 2;
+  static constexpr int STAGE = XROWS * XPITCH + SROWS * SPITCH;  // doubles per ring stage (even)
+  static constexpr int STAGES = 2;
+  static constexpr size_t SMEM = sizeof(double) * STAGE * STAGES;
+  static_assert(STAGE % 2 == 0, "ring stages must stay 16-byte aligned");
+  static_assert(XROWS + SROWS <= 64, "two staging rows per lane of the producer warp");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NDOF, int MODE, int CTAS>
+__global__ void __launch_bounds__(RingCfg<NDOF>::NT, CTAS)
+    elem_kernel_ring(Geo g, const __grid_constant__ KeParam<NDOF, true> ke, int nbx, int nby, int nbricks,
+                     const double* __restrict__ s, const unsigned char* __restrict__ mask,
+                     const unsigned char* __restrict__ flags, double bcdiag, const double* __restrict__ x,
+                     const double* __restrict__ b, const double* __restrict__ diag, double w, double* __restrict__ y,
+                     const double* __restrict__ dotv, double* __restrict__ partials) {
+  using C = RingCfg<NDOF>;
+  constexpr int BX = C::BX, BY = C::BY, BZ = C::BZ, NT = C::NT, TY = C::TY, XP = C::XPITCH, SP = C::SPITCH;
+  constexpr int LD = KeParam<NDOF, true>::LD;
+  extern __shared__ __align__(128) double ring[];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ double wred[3][NT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int my = (nbricks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // bricks blockIdx.x + t * gridDim.x
+  const long long Dx = (long long)(reinterpret_cast<uintptr_t>(x) >> 3), Ds = (long long)(reinterpret_cast<uintptr_t>(s) >> 3);
+  const long long xrow = (long long)g.NX * NDOF;  // doubles per node row
+
+  // stale-but-finite contract: the ring starts as zeros, later it only ever holds copied vector / density values
+  for (int p = tid; p < C::STAGE * C::STAGES; p += NT) ring[p] = 0.0;
+  if (tid == 0) {
+    for (int q = 0; q < C::STAGES; ++q) mbar_init(&full_bar[q], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before the async-proxy copies
+  __syncthreads();
+
+  // ---- producer (all lanes of warp 0): lane r copies staging rows r and r + 32 of brick t2 into ring stage t2 % 2
+  auto issue = [&](int t2) {
+    const int stg = t2 % C::STAGES;
+    double* su = ring + (size_t)stg * C::STAGE;
+    double* ss = su + C::XROWS * XP;
+    const int brick = (int)blockIdx.x + t2 * (int)gridDim.x;
+    const int bx = brick % nbx, rem = brick / nbx;
+    const int i0 = bx * BX, j0 = (rem % nby) * BY, kl0 = (rem / nby) * BZ;
+    uintptr_t src[2];
+    double* dst[2];
+    unsigned bytes[2] = {0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int r = lane + 32 * q;
+      if (r < C::XROWS) {
+        const int kl = kl0 - 1 + r / TY, j = j0 - 1 + r % TY, k = g.kz0 + kl;
+        const int ia = max(i0 - 1, 0), ib = min(i0 + BX + 1, g.NX);
+        // planes beyond the slab's upper halo (kl > nzl) are never needed and may not be mapped
+        if (j >= 0 && j < g.NY && k >= 0 && k < g.NZ && kl <= g.nzl && ib > ia) {
+          const long long rowb = ((long long)kl * g.NY + j) * xrow;
+          const long long D0 = Dx + rowb + (long long)(i0 - 1) * NDOF;                       // wanted first double (absolute index)
+          const long long lo = (Dx + rowb + (long long)ia * NDOF) & ~1LL;                    // 16-byte hull of the in-grid part
+          const long long hi = (Dx + rowb + (long long)ib * NDOF + 1) & ~1LL;
+          src[q] = (uintptr_t)lo << 3;
+          dst[q] = su + r * XP + (int)(lo - D0 + (D0 & 1));  // absolute double D lands at row[D - D0 + (D0 & 1)]
+          bytes[q] = (unsigned)(hi - lo) * 8u;
+        }
+      } else if (r < C::XROWS + C::SROWS) {
+        const int rs = r - C::XROWS;
+        const int el = kl0 - 1 + rs / (BY + 1), ej = j0 - 1 + rs % (BY + 1), ek = g.kz0 + el;
+        const int ia = max(i0 - 1, 0), ib = min(i0 + BX, g.nx);
+        // element layers above the last owned node plane belong to the next rank and are not needed
+        if (ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl && ib > ia) {
+          const long long rowb = ((long long)el * g.ny + ej) * g.nx;
+          const long long D0 = Ds + rowb + (i0 - 1);
+          const long long lo = (Ds + rowb + ia) & ~1LL, hi = (Ds + rowb + ib + 1) & ~1LL;
+          src[q] = (uintptr_t)lo << 3;
+          dst[q] = ss + rs * SP + (int)(lo - D0 + (D0 & 1));
+          bytes[q] = (unsigned)(hi - lo) * 8u;
+        }
+      }
+    }
+    const unsigned total = bytes[0] + bytes[1];
+    if (total) mbar_expect_tx(&full_bar[stg], total);  // arrive + expect: my bytes are announced before they can complete
+    else mbar_arrive(&full_bar[stg]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (bytes[q]) tma_load_1d(dst[q], reinterpret_cast<const void*>(src[q]), bytes[q], &full_bar[stg], false);
+  };
+  if (warp == 0)
+    for (int t2 = 0; t2 < C::STAGES && t2 < my; ++t2) issue(t2);
+
+  const int tx = tid % BX, ty = (tid / BX) % BY, tz = tid / (BX * BY);
+  const int pkx = (int)(((long long)g.NY * xrow) & 1), pjx = (int)(xrow & 1);       // row-shift parity per +1 plane / +1 row
+  const int pks = (int)(((long long)g.ny * g.nx) & 1), pjs = g.nx & 1;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+
+  for (int t = 0; t < my; ++t) {
+    const int stg = t % C::STAGES;
+    double* su = ring + (size_t)stg * C::STAGE;
+    double* ss = su + C::XROWS * XP;
+    const int brick = (int)blockIdx.x + t * (int)gridDim.x;
+    const int bx = brick % nbx, rem = brick / nbx;
+    const int i0 = bx * BX, j0 = (rem % nby) * BY, kl0 = (rem / nby) * BZ;
+    const int i = i0 + tx, j = j0 + ty, kl = kl0 + tz;
+    const bool valid = i < g.NX && j < g.NY && kl < g.nzl;
+    const long long ln = ((long long)kl * g.NY + j) * g.NX + i;
+    const bool flagged = mask && (flags ? flags[brick] != 0 : true);  // CTA-uniform
+    // density slots outside the grid / slab must read +0.0 (CTA-uniform test on the brick's element range)
+    const bool edge = i0 == 0 || i0 + BX > g.nx || j0 == 0 || j0 + BY > g.ny || g.kz0 + kl0 == 0 ||
+                      g.kz0 + kl0 + BZ > g.nzE || kl0 + BZ > g.nzl;
+
+    // ---- epilogue operands of this thread's rows: issued now, consumed after the FMA phase
+    double br[NDOF], dr[NDOF], dvr[NDOF], xm[NDOF];
+    bool mr[NDOF];
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d) {
+      const long long r = valid ? ln * NDOF + d : 0;
+      mr[d] = flagged && __ldg(mask + r);
+      xm[d] = mr[d] ? __ldg(x + r) : 0.0;  // Dirichlet rows (rare) need the unmasked x
+      br[d] = (MODE != EMODE_SPMV) ? __ldg(b + r) : 0.0;
+      dr[d] = (MODE == EMODE_JACOBI) ? __ldg(diag + r) : 1.0;
+      dvr[d] = (partials && dotv) ? __ldg(dotv + r) : 0.0;
+    }
+
+    mbar_wait(&full_bar[stg], (unsigned)((t / C::STAGES) & 1));
+
+    if (edge || flagged) {
+      if (edge) {
+        for (int p = tid; p < C::SROWS * C::SLEN; p += NT) {
+          const int rs = p / C::SLEN, c = p - rs * C::SLEN;
+          const int el = kl0 - 1 + rs / (BY + 1), ej = j0 - 1 + rs % (BY + 1), ek = g.kz0 + el, ei = i0 - 1 + c;
+          const bool ok = ei >= 0 && ei < g.nx && ej >= 0 && ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl;
+          if (!ok) ss[rs * SP + c + (int)((Ds + ((long long)el * g.ny + ej) * g.nx + (i0 - 1)) & 1)] = 0.0;
+        }
+      }
+      if (flagged) {
+        for (int p = tid; p < C::XROWS * C::XLEN; p += NT) {
+          const int r = p / C::XLEN, c = p - r * C::XLEN;
+          const int klr = kl0 - 1 + r / TY, jr = j0 - 1 + r % TY, kr = g.kz0 + klr, ir = i0 - 1 + c / NDOF;
+          if (ir >= 0 && ir < g.NX && jr >= 0 && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl) {
+            const long long rowb = ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF;
+            if (__ldg(mask + rowb + c)) su[r * XP + c + (int)((Dx + rowb) & 1)] = 0.0;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- FMA phase (same (dk, dj, di) order per element as elem_kernel -> bit-identical y)
+    // staged value of node (tx+1+di, ty+1+dj, tz+1+dk), component c: xb[|dk|&1][|dj|&1][((dk*TY + dj)*XP + di*NDOF + c]
+    const long long q0x = Dx + ((long long)kl * g.NY + j) * xrow + (long long)(i0 - 1) * NDOF;
+    const double* xc = su + ((tz + 1) * TY + (ty + 1)) * XP + (tx + 1) * NDOF;
+    const double* xb[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) xb[a][c] = xc + (int)((q0x + a * pkx + c * pjx) & 1);
+    // density of element (ox, oy, oz) of this node: sb[oz][oy][(oz*(BY+1) + oy)*SP + ox]
+    const long long q0s = Ds + ((long long)(kl - 1) * g.ny + (j - 1)) * g.nx + (i0 - 1);
+    const double* sc = ss + (tz * (BY + 1) + ty) * SP + tx;
+    const double* sb[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) sb[a][c] = sc + (int)((q0s + a * pks + c * pjs) & 1);
+
+    double tt[8][NDOF];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) tt[e][d] = 0.0;
+    double acc[NDOF];
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d) acc[d] = 0.0;
+    if (valid) {
+#pragma unroll
+      for (int dk = -1; dk <= 1; ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+          for (int di = -1; di <= 1; ++di) {
+            const double* up = xb[dk & 1][dj & 1] + (dk * TY + dj) * XP + di * NDOF;
+            double uv[NDOF];
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) uv[c] = up[c];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
+              const int ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
+              const int bxx = ax + di, byy = ay + dj, bzz = az + dk;
+              if (bxx < 0 || bxx > 1 || byy < 0 || byy > 1 || bzz < 0 || bzz > 1) continue;
+              const int a = ax + 2 * ay + 4 * az, bn = bxx + 2 * byy + 4 * bzz;
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c)
+#pragma unroll
+                for (int d = 0; d < NDOF; ++d) tt[e][d] = fma(ke.v[(a * NDOF + d) * LD + bn * NDOF + c], uv[c], tt[e][d]);
+            }
+          }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ox = e & 1, oy = (e >> 1) & 1, oz = (e >> 2) & 1;
+        const double se = sb[oz][oy][(oz * (BY + 1) + oy) * SP + ox];
+#pragma unroll
+        for (int d = 0; d < NDOF; ++d) acc[d] = fma(se, tt[e][d], acc[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d) {
+        const long long r = ln * NDOF + d;
+        const double xr = mr[d] ? xm[d] : xb[0][0][d];
+        const double ax = mr[d] ? bcdiag * xr : acc[d];
+        double out;
+        if (MODE == EMODE_SPMV) out = ax;
+        else if (MODE == EMODE_RESID) out = br[d] - ax;
+        else out = xr + w * ((br[d] - ax) / dr[d]);
+        y[r] = out;
+        if (partials) {
+          d0 = fma(out, xr, d0);
+          d1 = fma(xr, dvr[d], d1);
+          d2 = fma(out, dvr[d], d2);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with ring stage stg
+    if (warp == 0 && t + C::STAGES < my) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads / patches before the async-proxy refill
+      issue(t + C::STAGES);
+    }
+  }
+  if (partials) {
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (lane == 0) wred[0][warp] = d0, wred[1][warp] = d1, wred[2][warp] = d2;
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int v = 0; v < NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
+      partials[3 * (long long)blockIdx.x] = s0;
+      partials[3 * (long long)blockIdx.x + 1] = s1;
+      partials[3 * (long long)blockIdx.x + 2] = s2;
+    }
+  }
+}
+
+// flags[brick] = 1 if the staged region of the ring layout's brick (32 x 4 x 2 nodes + 1-node apron) holds a masked dof
+__global__ void __launch_bounds__(256) elem_brickflags_kernel(Geo g, int nbx, int nby, const unsigned char* __restrict__ mask,
+                                                               unsigned char* __restrict__ flags) {
+  constexpr int BX = 32, BY = 4, BZ = 2, TX = BX + 2, TY = BY + 2, TZ = BZ + 2;
+  const int brick = blockIdx.x;
+  const int i0 = (brick % nbx) * BX, j0 = ((brick / nbx) % nby) * BY, kl0 = (brick / nbx / nby) * BZ;
+  const int len = TX * g.ndof;
+  int any = 0;
+  for (int p = threadIdx.x; p < TZ * TY * len; p += 256) {
+    const int r = p / len, c = p - r * len;
+    const int kl = kl0 - 1 + r / TY, j = j0 - 1 + r % TY, k = g.kz0 + kl, i = i0 - 1 + c / g.ndof;
+    if (i >= 0 && i < g.NX && j >= 0 && j < g.NY && k >= 0 && k < g.NZ && kl <= g.nzl)
+      any |= mask[(((long long)kl * g.NY + j) * g.NX + (i0 - 1)) * g.ndof + c] != 0;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[brick] = any ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// y-marching tensor-core layout (variant 6, 3-D, ndof = 3): FP64 DMMA with register-resident Ke and in-register
+// accumulation -- no scatter buffer, no gather phase.
+//
+// The DFMA layouts spend 3 instructions per multiply-add (DFMA + the LDCU that feeds its Ke operand + shared loads /
+// addressing; ncu: issue slots saturated at 48 % FP64-pipe activity).  DMMA.8x8x4 does 256 multiply-adds per instruction
+// with the Ke operand held in registers (each lane keeps 1/32 of every fragment).  Arrangement:
+//   * the 8 columns of a DMMA are 8 CONSECUTIVE ELEMENT ROWS (j .. j+7) of one element column (ei, ek); B fragments are
+//     the element displacements, read from staged node rows in shared memory;
+//   * the 8 rows are the 6 rows (ay, d) of Ke that belong to one (ax, az) corner group (+ 2 zero rows): the product of
+//     group (ax, az) with element column (ei, ek) is that column's contribution to NODE column (ei + ax, ek + az), so the
+//     <= 4 contributions of a node column accumulate in the same registers (scaled per element by s_e on the way in);
+//   * what remains is the shift by ay along the DMMA columns (= along y): node row j takes the ay = 0 row of column j
+//     and the ay = 1 row of column j - 1 -- two warp shuffles, and one carried value into the next batch of 8 rows.
+//     A CTA owns a strip of 32 x 2 node columns and marches along y through the whole grid, so that carry never crosses
+//     a CTA and no element is computed twice.
+// Staging is the bulk-copy ring of the layouts above (per step 36 node rows + 24 density rows, one per lane of warp 0).
+// Tensor-core accumulation order differs from the DFMA layouts: y agrees to rounding, not bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+struct YmCfg {
+  static constexpr int BX = 32, BZ = 2, JB = 8, NT = 256, NDOF = 3;
+  static constexpr int XLEN = (BX + 2) * NDOF, XP = 108;     // node-row pitch: 102 + shift + round-up, 12 mod 16 (bank spread)
+  static constexpr int SLEN = BX + 1, SP = 36;
+  static constexpr int XROWS = (BZ + 2) * (JB + 1), SROWS = (BZ + 1) * JB;   // 36 + 24 staging rows per step
+  static constexpr int STAGE = XROWS * XP + SROWS * SP, STAGES = 2;
+  static constexpr int OUTW = 8 * NDOF;                      // outputs of a warp per node row
+  static constexpr int SMEM_DOUBLES = STAGE * STAGES + (NT / 32) * (JB * OUTW + OUTW) + 24 * 24;
+  static_assert(STAGE % 2 == 0 && XP % 2 == 0 && SP % 2 == 0, "16-byte aligned staging rows");
+  static_assert(XROWS + SROWS <= 64, "two staging rows per lane of the producer warp");
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(YmCfg::NT, 2)
+    elem_kernel_ym(Geo g, const __grid_constant__ KeParam<3, true> ke, int nsteps, const double* __restrict__ s,
+                   const unsigned char* __restrict__ mask, const unsigned char* __restrict__ flags, double bcdiag,
+                   const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ diag, double w,
+                   double* __restrict__ y, const double* __restrict__ dotv, double* __restrict__ partials) {
+  using C = YmCfg;
+  constexpr int NDOF = 3, XP = C::XP, SP = C::SP, JB = C::JB, NT = C::NT;
+  extern __shared__ __align__(128) double ring[];
+  double* sOut = ring + C::STAGE * C::STAGES;                 // [warp][JB][24] finished rows, then [warp][24] carry
+  double* sCarry = sOut + (NT / 32) * JB * C::OUTW;
+  double* sKe = sCarry + (NT / 32) * C::OUTW;
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ double wred[3][NT / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * C::BX, kl0 = blockIdx.y * C::BZ;
+  const long long Dx = (long long)(reinterpret_cast<uintptr_t>(x) >> 3), Ds = (long long)(reinterpret_cast<uintptr_t>(s) >> 3);
+  const long long xrow = (long long)g.NX * NDOF;
+
+  for (int p = tid; p < C::STAGE * C::STAGES; p += NT) ring[p] = 0.0;   // stale-but-finite contract (see elem_kernel_ring)
+  for (int p = tid; p < (NT / 32) * C::OUTW; p += NT) sCarry[p] = 0.0;
+  for (int p = tid; p < 24 * 24; p += NT) sKe[p] = ke.v[p];
+  if (tid == 0) {
+    for (int q = 0; q < C::STAGES; ++q) mbar_init(&full_bar[q], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  // ---- producer (warp 0): staging rows of step t2 -> ring stage t2 % 2.  Node rows: plane p (kl0-1+p), row 8 t2 + rr;
+  //      density rows: layer l (kl0-1+l), element row 8 t2 + rr
+  auto issue = [&](int t2) {
+    const int stg = t2 % C::STAGES;
+    double* su = ring + (size_t)stg * C::STAGE;
+    double* ss = su + C::XROWS * XP;
+    uintptr_t src[2];
+    double* dst[2];
+    unsigned bytes[2] = {0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int r = lane + 32 * q;
+      if (r < C::XROWS) {
+        const int kl = kl0 - 1 + r / (JB + 1), j = JB * t2 + r % (JB + 1), k = g.kz0 + kl;
+        const int ia = max(i0 - 1, 0), ib = min(i0 + C::BX + 1, g.NX);
+        if (j < g.NY && k >= 0 && k < g.NZ && kl <= g.nzl && ib > ia) {
+          const long long rowb = ((long long)kl * g.NY + j) * xrow;
+          const long long D0 = Dx + rowb + (long long)(i0 - 1) * NDOF;
+          const long long lo = (Dx + rowb + (long long)ia * NDOF) & ~1LL, hi = (Dx + rowb + (long long)ib * NDOF + 1) & ~1LL;
+          src[q] = (uintptr_t)lo << 3;
+          dst[q] = su + r * XP + (int)(lo - D0 + (D0 & 1));
+          bytes[q] = (unsigned)(hi - lo) * 8u;
+        }
+      } else if (r < C::XROWS + C::SROWS) {
+        const int rs = r - C::XROWS;
+        const int el = kl0 - 1 + rs / JB, ej = JB * t2 + rs % JB, ek = g.kz0 + el;
+        const int ia = max(i0 - 1, 0), ib = min(i0 + C::BX, g.nx);
+        if (ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl && ib > ia) {
+          const long long rowb = ((long long)el * g.ny + ej) * g.nx;
+          const long long D0 = Ds + rowb + (i0 - 1);
+          const long long lo = (Ds + rowb + ia) & ~1LL, hi = (Ds + rowb + ib + 1) & ~1LL;
+          src[q] = (uintptr_t)lo << 3;
+          dst[q] = ss + rs * SP + (int)(lo - D0 + (D0 & 1));
+          bytes[q] = (unsigned)(hi - lo) * 8u;
+        }
+      }
+    }
+    const unsigned total = bytes[0] + bytes[1];
+    if (total) mbar_expect_tx(&full_bar[stg], total);
+    else mbar_arrive(&full_bar[stg]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (bytes[q]) tma_load_1d(dst[q], reinterpret_cast<const void*>(src[q]), bytes[q], &full_bar[stg], false);
+  };
+  if (warp == 0)
+    for (int t2 = 0; t2 < C::STAGES && t2 < nsteps; ++t2) issue(t2);
+
+  // ---- consumer role of this warp: node columns i = iw .. iw+7 of plane kl
+  const int wx = warp & 3, wz = warp >> 2;
+  const int iw = i0 + 8 * wx, kl = kl0 + wz;
+  const bool wactive = iw < g.NX && kl < g.nzl;
+  const int gq = lane >> 2, q4 = lane & 3;   // DMMA fragment coordinates: row / column group, k index
+  // A fragments: group (ax, az), row gq = (ay, d) (rows 6, 7 are zero), k = 4 ks + q4
+  double af[2][2][6];
+#pragma unroll
+  for (int az = 0; az < 2; ++az)
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax)
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks) {
+        const int ay = gq / 3, d = gq - 3 * ay;
+        const int a = ax + 2 * ay + 4 * az;
+        af[az][ax][ks] = gq < 6 ? sKe[(a * NDOF + d) * 24 + 4 * ks + q4] : 0.0;
+      }
+  // B fragment offsets (doubles inside a ring stage, element column offset excluded): k index kk = 4 ks + q4 = 3 bn + c,
+  // column gq = element row; node (bx, gq + by, bz) of the element, layer selector az (element layer = kl - az)
+  const int P0 = (int)((Dx + ((long long)(kl0 - 1) * g.NY) * xrow + (long long)(i0 - 1) * NDOF) & 1);
+  const int pkx = (int)(((long long)g.NY * xrow) & 1), pjx = (int)(xrow & 1);
+  int boff[2][6];
+#pragma unroll
+  for (int az = 0; az < 2; ++az)
+#pragma unroll
+    for (int ks = 0; ks < 6; ++ks) {
+      const int kk = 4 * ks + q4, bn = kk / 3, c = kk - 3 * bn;
+      const int bx = bn & 1, by = (bn >> 1) & 1, bz = bn >> 2;
+      const int p = wz + 1 - az + bz, row = gq + by;
+      boff[az][ks] = (p * (JB + 1) + row) * XP + bx * NDOF + c + ((P0 + p * pkx + row * pjx) & 1);
+    }
+  const int Ps0 = (int)((Ds + ((long long)(kl0 - 1) * g.ny) * g.nx + (i0 - 1)) & 1);
+  const int pks = (int)(((long long)g.ny * g.nx) & 1), pjs = g.nx & 1;
+  int soff[2][2];
+#pragma unroll
+  for (int az = 0; az < 2; ++az)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int l = wz + 1 - az, row = 2 * q4 + h;
+      soff[az][h] = C::XROWS * XP + (l * JB + row) * SP + ((Ps0 + l * pks + row * pjs) & 1);
+    }
+  double* myOut = sOut + warp * JB * C::OUTW;
+  double* myCarry = sCarry + warp * C::OUTW;
+  const int nbxg = gridDim.x;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+
+  for (int t = 0; t <= nsteps; ++t) {
+    const bool flush = t == nsteps;       // last pass: only the carried row (node row 8 nsteps, when it exists)
+    if (flush && (JB * nsteps >= g.NY)) break;
+    const int stg = t % C::STAGES;
+    double* su = ring + (size_t)stg * C::STAGE;
+    const int j0 = JB * t;
+    bool flagged = false;
+    if (!flush) {
+      flagged = mask && (flags ? flags[((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps + t] != 0 : true);
+      const bool edge = i0 == 0 || i0 + C::BX > g.nx || j0 + JB > g.ny || g.kz0 + kl0 == 0 || g.kz0 + kl0 + C::BZ > g.nzE ||
+                        kl0 + C::BZ > g.nzl;
+      mbar_wait(&full_bar[stg], (unsigned)((t / C::STAGES) & 1));
+      if (edge || flagged) {
+        double* ss = su + C::XROWS * XP;
+        if (edge) {
+          for (int p = tid; p < C::SROWS * C::SLEN; p += NT) {
+            const int rs = p / C::SLEN, c = p - rs * C::SLEN;
+            const int el = kl0 - 1 + rs / JB, ej = j0 + rs % JB, ek = g.kz0 + el, ei = i0 - 1 + c;
+            const bool ok = ei >= 0 && ei < g.nx && ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl;
+            if (!ok) ss[rs * SP + c + (int)((Ds + ((long long)el * g.ny + ej) * g.nx + (i0 - 1)) & 1)] = 0.0;
+          }
+        }
+        if (flagged) {
+          for (int p = tid; p < C::XROWS * C::XLEN; p += NT) {
+            const int r = p / C::XLEN, c = p - r * C::XLEN;
+            const int klr = kl0 - 1 + r / (JB + 1), jr = j0 + r % (JB + 1), kr = g.kz0 + klr, ir = i0 - 1 + c / NDOF;
+            if (ir >= 0 && ir < g.NX && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl) {
+              const long long rowb = ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF;
+              if (__ldg(mask + rowb + c)) su[r * XP + c + (int)((Dx + rowb) & 1)] = 0.0;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    if (wactive) {
+      if (!flush) {
+        // ---- DMMA phase: element columns ei = iw-1 .. iw+7, layers kl-1 (az = 1) and kl (az = 0); node column ei is
+        //      finished once element column ei has been processed
+        double ynext[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ex = -1; ex < 8; ++ex) {
+          double ycur[2] = {ynext[0], ynext[1]};
+          ynext[0] = ynext[1] = 0.0;
+          const int coloff = (8 * wx + ex + 1) * NDOF;
+#pragma unroll
+          for (int az = 0; az < 2; ++az) {
+            double bv[6];
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks) bv[ks] = su[boff[az][ks] + coloff];
+            const double s0 = su[soff[az][0] + 8 * wx + ex + 1], s1 = su[soff[az][1] + 8 * wx + ex + 1];
+            if (ex >= 0) {   // ax = 0: this element column's own node column
+              double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+              for (int ks = 0; ks < 6; ++ks) dmma884(c0, c1, af[az][0][ks], bv[ks]);
+              ycur[0] = fma(s0, c0, ycur[0]);
+              ycur[1] = fma(s1, c1, ycur[1]);
+            }
+            if (ex < 7) {    // ax = 1: the node column to the right
+              double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+              for (int ks = 0; ks < 6; ++ks) dmma884(c0, c1, af[az][1][ks], bv[ks]);
+              ynext[0] = fma(s0, c0, ynext[0]);
+              ynext[1] = fma(s1, c1, ynext[1]);
+            }
+          }
+          if (ex >= 0) {
+            // ---- node column di = ex finished: lane (row gq = (ay, d), cols 2 q4, 2 q4 + 1).  Node row c takes (ay = 0,
+            //      col c) + (ay = 1, col c - 1); col -1 is the value carried from the previous step
+            const int srcrow = (gq % 3 + 3) * 4;                              // lane base of row (ay = 1, d)
+            const double t0 = __shfl_sync(0xffffffffu, ycur[1], srcrow + ((q4 + 3) & 3));   // (1, d), col 2 q4 - 1
+            const double t1 = __shfl_sync(0xffffffffu, ycur[0], srcrow + q4);               // (1, d), col 2 q4
+            if (gq < 3) {
+              const double cin = myCarry[ex * NDOF + gq];
+              myOut[(2 * q4) * C::OUTW + ex * NDOF + gq] = ycur[0] + (q4 == 0 ? cin : t0);
+              myOut[(2 * q4 + 1) * C::OUTW + ex * NDOF + gq] = ycur[1] + t1;
+            }
+            __syncwarp();
+            if (gq >= 3 && gq < 6 && q4 == 3) myCarry[ex * NDOF + gq - 3] = ycur[1];   // (1, d), col 7 -> next step's row 0
+          }
+        }
+      } else {
+        for (int p = lane; p < JB * C::OUTW; p += 32) myOut[p] = p < C::OUTW ? myCarry[p] : 0.0;
+      }
+      __syncwarp();
+    }
+    if (!flush) {
+      __syncthreads();  // every warp is done with ring stage stg (the epilogue below reads global memory only)
+      if (warp == 0 && t + C::STAGES < nsteps) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(t + C::STAGES);
+      }
+    }
+    if (wactive) {
+      // ---- epilogue: 8 node rows x 24 contiguous doubles (8 nodes x 3 dofs) of this warp; lane < 24 owns one column of
+      //      them.  All loads of 4 rows are issued before the first use.
+      const int nrows = flush ? 1 : JB;
+      const bool act = lane < C::OUTW && iw + lane / NDOF < g.NX;
+      const long long r0 = (((long long)kl * g.NY + j0) * g.NX + iw) * NDOF + lane;
+      const bool masked_step = (flagged || flush) && mask;   // warp-uniform
+#pragma unroll
+      for (int h = 0; h < JB; h += 4) {
+        double xr[4], br[4], dr[4], dv[4];
+        bool ok[4], mr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ok[c] = act && h + c < nrows && j0 + h + c < g.NY;
+          const long long r = ok[c] ? r0 + (long long)(h + c) * xrow : 0;
+          xr[c] = (MODE == EMODE_JACOBI || partials || masked_step) ? __ldg(x + r) : 0.0;
+          br[c] = (MODE != EMODE_SPMV) ? __ldg(b + r) : 0.0;
+          dr[c] = (MODE == EMODE_JACOBI) ? __ldg(diag + r) : 1.0;
+          dv[c] = (partials && dotv) ? __ldg(dotv + r) : 0.0;
+          mr[c] = masked_step && __ldg(mask + r);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (ok[c]) {
+            const double ax = mr[c] ? bcdiag * xr[c] : myOut[(h + c) * C::OUTW + lane];
+            double out;
+            if (MODE == EMODE_SPMV) out = ax;
+            else if (MODE == EMODE_RESID) out = br[c] - ax;
+            else out = xr[c] + w * ((br[c] - ax) / dr[c]);
+            y[r0 + (long long)(h + c) * xrow] = out;
+            if (partials) {
+              d0 = fma(out, xr[c], d0);
+              d1 = fma(xr[c], dv[c], d1);
+              d2 = fma(out, dv[c], d2);
+            }
+          }
+        }
+      }
+    }
+    if (flush) break;
+  }
+  if (partials) {
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (lane == 0) wred[0][warp] = d0, wred[1][warp] = d1, wred[2][warp] = d2;
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int v = 0; v < NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
+      const long long bid = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+      partials[3 * bid] = s0;
+      partials[3 * bid + 1] = s1;
+      partials[3 * bid + 2] = s2;
+    }
+  }
+}
+
+// flags[(bz * nbx + bx) * nsteps + t] = 1 iff the rows staged by CTA (bx, bz) of the y-marching layout in step t hold a masked dof
+__global__ void __launch_bounds__(256) elem_ymflags_kernel(Geo g, int nsteps, const unsigned char* __restrict__ mask,
+                                                            unsigned char* __restrict__ flags) {
+  using C = YmCfg;
+  const int t = blockIdx.x, i0 = blockIdx.y * C::BX, kl0 = blockIdx.z * C::BZ;   // grid (nsteps, nbx, nbz)
+  int any = 0;
+  for (int p = threadIdx.x; p < C::XROWS * C::XLEN; p += 256) {
+    const int r = p / C::XLEN, c = p - r * C::XLEN;
+    const int kl = kl0 - 1 + r / (C::JB + 1), j = C::JB * t + r % (C::JB + 1), k = g.kz0 + kl, i = i0 - 1 + c / 3;
+    if (i >= 0 && i < g.NX && j < g.NY && k >= 0 && k < g.NZ && kl <= g.nzl)
+      any |= mask[(((long long)kl * g.NY + j) * g.NX + (i0 - 1)) * 3 + c] != 0;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = any ? 1 : 0;
+}
+
+static int sm_count_elem() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+static void ring_bricks(const Geo& g, int& nbx, int& nby, int& nbz) {
+  nbx = (g.NX + 31) / 32;
+  nby = (g.NY + 3) / 4;
+  nbz = (g.nzl + 1) / 2;
+}
+
+static void ym_grid(const Geo& g, int& nbx, int& nbz, int& nsteps) {
+  nbx = (g.NX + YmCfg::BX - 1) / YmCfg::BX;
+  nbz = (g.nzl + YmCfg::BZ - 1) / YmCfg::BZ;
+  nsteps = (g.ny + YmCfg::JB - 1) / YmCfg::JB;
+}
+
+extern "C" long long pmb_elem_brickflags_bytes(const pmb_grid* p, int variant) {
+  if (validate_grid(p, "pmb_elem_brickflags_bytes")) return -1;
+  Geo g = make_geo(p);
+  if (variant == 6) {
+    int nbx, nbz, nsteps;
+    ym_grid(g, nbx, nbz, nsteps);
+    return (long long)nbx * nbz * nsteps;
+  }
+  int nbx, nby, nbz;
+  ring_bricks(g, nbx, nby, nbz);
+  return (long long)nbx * nby * nbz;
+}
+
+extern "C" int pmb_elem_brickflags(const pmb_grid* p, int variant, const unsigned char* bcmask, unsigned char* flags, void* stream) {
+  if (validate_grid(p, "pmb_elem_brickflags")) return 1;
+  PMB_REQUIRE(bcmask && flags, "pmb_elem_brickflags: NULL pointer argument");
+  PMB_REQUIRE(p->nz > 0, "pmb_elem_brickflags: 3-D grids only");
+  PMB_REQUIRE(variant == 4 || variant == 5 || variant == 6, "pmb_elem_brickflags: layout %d takes no flags", variant);
+  Geo g = make_geo(p);
+  if (variant == 6) {
+    PMB_REQUIRE(g.ndof == 3, "pmb_elem_brickflags: layout 6 is ndof = 3 only");
+    int nbx, nbz, nsteps;
+    ym_grid(g, nbx, nbz, nsteps);
+    PMB_REQUIRE(nbx <= 65535 && nbz <= 65535, "pmb_elem_brickflags: grid too large");
+    elem_ymflags_kernel<<<dim3(nsteps, nbx, nbz), 256, 0, (cudaStream_t)stream>>>(g, nsteps, bcmask, flags);
+    PMB_CHECK_LAUNCH("pmb_elem_brickflags");
+    return 0;
+  }
+  int nbx, nby, nbz;
+  ring_bricks(g, nbx, nby, nbz);
+  const long long nb = (long long)nbx * nby * nbz;
+  PMB_REQUIRE(nb < 2147483647LL, "pmb_elem_brickflags: too many bricks");
+  elem_brickflags_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g, nbx, nby, bcmask, flags);
+  PMB_CHECK_LAUNCH("pmb_elem_brickflags");
+  return 0;
+}
+
 // planes per CTA of the tensor-core layout: few enough CTAs per wave lost to the tail, little redundant layer work
 // (every CTA computes one extra element layer)
 static int mma_zl(const Geo& g) {
@@ -678,38 +1343,43 @@ static dim3 elem_grid(const Geo& g) {
   return dim3((g.NX + BX - 1) / BX, (g.NY + BY - 1) / BY, (g.nzl + BZ - 1) / BZ);
 }
 
-// ---- layout selection (3-D, ndof 1 or 3): 0 = one node per thread on a 32x4x2 brick (elem_kernel), 1 / 2 = z-marching
-//      32x8 / 32x4 columns with ring-buffered planes (elem_kernel_zm), 3 = FP64 tensor-core layout (elem_kernel_mma,
-//      ndof 3 only; other ndof fall back to 0).  Chosen per process by pmb_elem_set_variant() /
-//      PMB_ELEM_VARIANT or measured by pmb_elem_autotune(); all layouts produce bit-identical y.
-enum { PMB_ELEM_VARIANTS = 4 };
-static int g_elem_variant[4] = {-1, -1, -1, -1};  // per dofs-per-node (the FMA phase is 9x heavier for ndof = 3 than for 1)
-static int& elem_variant(int ndof) {
-  if (g_elem_variant[0] < 0) {
-    const char* e = getenv("PMB_ELEM_VARIANT");
-    const int v = (e && e[0] >= '0' && e[0] < '0' + PMB_ELEM_VARIANTS) ? e[0] - '0' : 0;
-    for (int i = 0; i < 4; ++i) g_elem_variant[i] = v;
-  }
-  return g_elem_variant[ndof >= 1 && ndof <= 3 ? ndof : 0];
-}
-extern "C" int pmb_elem_set_variant(int v) {
-  PMB_REQUIRE(v >= 0 && v < PMB_ELEM_VARIANTS, "pmb_elem_set_variant: variant %d not in 0..%d", v, PMB_ELEM_VARIANTS - 1);
-  for (int i = 0; i < 4; ++i) g_elem_variant[i] = v;
-  return 0;
-}
-extern "C" int pmb_elem_get_variant(int ndof) { return elem_variant(ndof); }
+// ---- layouts of the 3-D kernel (ndof 1 or 3; 2-D grids and ndof 2 always run layout 0): 0 = one node per thread on a
+//      32x4x2 brick (elem_kernel), 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered planes (elem_kernel_zm),
+//      3 = FP64 tensor-core layout (elem_kernel_mma, ndof 3 only; other ndof run 0), 4 / 5 = persistent CTAs with bulk-copy
+//      staged bricks (elem_kernel_ring) at 3 / 2 CTAs per SM, 6 = y-marching FP64 tensor-core layout with in-register
+//      accumulation (elem_kernel_ym, ndof 3 only).  The layout is a field of the caller's pmb_elem_op: no process-wide state.
+//      Layouts 0, 1, 2, 4, 5 produce bit-identical y; 3 and 6 (tensor-core accumulation order) agree to rounding.
+enum { PMB_ELEM_VARIANTS = 7 };
 extern "C" int pmb_elem_num_variants(void) { return PMB_ELEM_VARIANTS; }
+
+static int effective_variant(const Geo& g, int variant) {
+  if (!g.dim3 || g.ndof == 2) return 0;
+  if ((variant == 3 || variant == 6) && g.ndof != 3) return 0;
+  return variant;
+}
 
 static dim3 elem_grid_any(const Geo& g, int variant) {
   if (!g.dim3) return elem_grid<false>(g);
+  variant = effective_variant(g, variant);
   switch (variant) {
     case 1: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 7) / 8, (g.nzl + ZM_L - 1) / ZM_L);
     case 2: return dim3((g.NX + ZM_BX - 1) / ZM_BX, (g.NY + 3) / 4, (g.nzl + ZM_L - 1) / ZM_L);
-    case 3:
-      if (g.ndof == 3) {
-        const int zl = mma_zl(g);
-        return dim3((g.NX + MM_NXT - 1) / MM_NXT, (g.NY + MM_NYT - 1) / MM_NYT, (g.nzl + zl - 1) / zl);
-      }
+    case 3: {
+      const int zl = mma_zl(g);
+      return dim3((g.NX + MM_NXT - 1) / MM_NXT, (g.NY + MM_NYT - 1) / MM_NYT, (g.nzl + zl - 1) / zl);
+    }
+    case 4:
+    case 5: {
+      int nbx, nby, nbz;
+      ring_bricks(g, nbx, nby, nbz);
+      const long long nb = (long long)nbx * nby * nbz, cap = (variant == 4 ? 3LL : 2LL) * sm_count_elem();
+      return dim3((unsigned)(nb < cap ? nb : cap), 1, 1);
+    }
+    case 6: {
+      int nbx, nbz, nsteps;
+      ym_grid(g, nbx, nbz, nsteps);
+      return dim3(nbx, nbz, 1);
+    }
   }
   return elem_grid<true>(g);
 }
@@ -727,12 +1397,14 @@ extern "C" long long pmb_elem_ws_doubles(const pmb_grid* p) {
 }
 
 template <int NDOF, bool DIM3, int MODE>
-static int launch_elem(const Geo& g, const double* Ke_host, const double* s, const unsigned char* mask, double bcdiag,
-                       const double* x, const double* b, const double* diag, double w, double* y, const double* dotv,
-                       double* dot_out, double* ws, cudaStream_t st) {
+static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, const double* b, const double* diag, double w,
+                       double* y, const double* dotv, double* dot_out, double* ws, cudaStream_t st) {
   KeParam<NDOF, DIM3> ke;
-  memcpy(ke.v, Ke_host, sizeof(ke.v));
-  const int variant = (DIM3 && NDOF != 2) ? elem_variant(NDOF) : 0;
+  memcpy(ke.v, op->Ke_host, sizeof(ke.v));
+  const double* s = op->s;
+  const unsigned char* mask = op->bcmask;
+  const double bcdiag = op->bcdiagval;
+  const int variant = effective_variant(g, op->variant);
   dim3 grid = elem_grid_any(g, variant);
   double* part = dot_out ? ws : nullptr;
   if constexpr (DIM3 && NDOF != 2) {
@@ -740,7 +1412,7 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
       elem_kernel_zm<NDOF, MODE, 8, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
     else if (variant == 2)
       elem_kernel_zm<NDOF, MODE, 4, 4><<<grid, 128, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
-    else if (variant == 3 && NDOF == 3) {
+    else if (variant == 3) {
       if constexpr (NDOF == 3) {
         constexpr size_t smem = sizeof(double) * MM_SMEM_DOUBLES;
         static bool configured = false;
@@ -751,8 +1423,41 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
         }
         elem_kernel_mma<MODE><<<grid, MM_NT, smem, st>>>(g, ke, mma_zl(g), s, mask, bcdiag, x, b, diag, w, y, dotv, part);
       }
-    }
-    else
+    } else if (variant == 6) {
+      if constexpr (NDOF == 3) {
+        constexpr size_t smem = sizeof(double) * YmCfg::SMEM_DOUBLES;
+        static bool configured = false;
+        if (!configured) {
+          cudaError_t e = cudaFuncSetAttribute(elem_kernel_ym<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return pmb_set_error("elem_kernel_ym attribute: %s", cudaGetErrorString(e));
+          configured = true;
+        }
+        int nbx, nbz, nsteps;
+        ym_grid(g, nbx, nbz, nsteps);
+        PMB_REQUIRE(nbz <= 65535, "pmb_elem_spmv: slab too tall for the y-marching layout");
+        elem_kernel_ym<MODE><<<grid, YmCfg::NT, smem, st>>>(g, ke, nsteps, s, mask, op->brickflags, bcdiag, x, b, diag, w, y, dotv, part);
+      }
+    } else if (variant == 4 || variant == 5) {
+      using C = RingCfg<NDOF>;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(elem_kernel_ring<NDOF, MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(elem_kernel_ring<NDOF, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return pmb_set_error("elem_kernel_ring attribute: %s", cudaGetErrorString(e));
+        configured = true;
+      }
+      int nbx, nby, nbz;
+      ring_bricks(g, nbx, nby, nbz);
+      const long long nb = (long long)nbx * nby * nbz;
+      PMB_REQUIRE(nb < 2147483647LL, "pmb_elem_spmv: too many bricks");
+      if (variant == 4)
+        elem_kernel_ring<NDOF, MODE, 3><<<grid, C::NT, C::SMEM, st>>>(g, ke, nbx, nby, (int)nb, s, mask, op->brickflags, bcdiag, x, b, diag,
+                                                                      w, y, dotv, part);
+      else
+        elem_kernel_ring<NDOF, MODE, 2><<<grid, C::NT, C::SMEM, st>>>(g, ke, nbx, nby, (int)nb, s, mask, op->brickflags, bcdiag, x, b, diag,
+                                                                      w, y, dotv, part);
+    } else
       elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
   } else {
     elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
@@ -766,22 +1471,23 @@ static int launch_elem(const Geo& g, const double* Ke_host, const double* s, con
 }
 
 template <int NDOF, bool DIM3>
-static int dispatch_elem(int mode, const Geo& g, const double* Ke_host, const double* s, const unsigned char* mask,
-                         double bcdiag, const double* x, const double* b, const double* diag, double w, double* y,
-                         const double* dotv, double* dot_out, double* ws, cudaStream_t st) {
+static int dispatch_elem(int mode, const Geo& g, const pmb_elem_op* op, const double* x, const double* b, const double* diag,
+                         double w, double* y, const double* dotv, double* dot_out, double* ws, cudaStream_t st) {
   switch (mode) {
-    case EMODE_SPMV: return launch_elem<NDOF, DIM3, EMODE_SPMV>(g, Ke_host, s, mask, bcdiag, x, b, diag, w, y, dotv, dot_out, ws, st);
-    case EMODE_RESID: return launch_elem<NDOF, DIM3, EMODE_RESID>(g, Ke_host, s, mask, bcdiag, x, b, diag, w, y, dotv, dot_out, ws, st);
-    case EMODE_JACOBI: return launch_elem<NDOF, DIM3, EMODE_JACOBI>(g, Ke_host, s, mask, bcdiag, x, b, diag, w, y, dotv, dot_out, ws, st);
+    case EMODE_SPMV: return launch_elem<NDOF, DIM3, EMODE_SPMV>(g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+    case EMODE_RESID: return launch_elem<NDOF, DIM3, EMODE_RESID>(g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+    case EMODE_JACOBI: return launch_elem<NDOF, DIM3, EMODE_JACOBI>(g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
   }
   return pmb_set_error("pmb_elem_spmv: unknown mode %d", mode);
 }
 
-extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const double* Ke_host, const double* s, const unsigned char* bcmask,
-                             double bcdiagval, const double* x, const double* b, const double* diag, double w, double* y,
-                             const double* dotv, double* dot_out, double* ws, void* stream) {
+extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const pmb_elem_op* op, const double* x, const double* b,
+                             const double* diag, double w, double* y, const double* dotv, double* dot_out, double* ws,
+                             void* stream) {
   if (validate_grid(p, "pmb_elem_spmv")) return 1;
-  PMB_REQUIRE(Ke_host && s && x && y, "pmb_elem_spmv: NULL pointer argument");
+  PMB_REQUIRE(op && op->Ke_host && op->s && x && y, "pmb_elem_spmv: NULL pointer argument");
+  PMB_REQUIRE(op->variant >= 0 && op->variant < PMB_ELEM_VARIANTS, "pmb_elem_spmv: variant %d not in 0..%d", op->variant,
+              PMB_ELEM_VARIANTS - 1);
   PMB_REQUIRE(x != y, "pmb_elem_spmv: y must not alias x");
   PMB_REQUIRE(mode == EMODE_SPMV || b, "pmb_elem_spmv: b required for residual / Jacobi");
   PMB_REQUIRE(mode != EMODE_JACOBI || diag, "pmb_elem_spmv: diag required for Jacobi");
@@ -790,40 +1496,55 @@ extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const double* Ke_host,
   cudaStream_t st = (cudaStream_t)stream;
   if (g.dim3) {
     switch (g.ndof) {
-      case 1: return dispatch_elem<1, true>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
-      case 2: return dispatch_elem<2, true>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
-      case 3: return dispatch_elem<3, true>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 1: return dispatch_elem<1, true>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 2: return dispatch_elem<2, true>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 3: return dispatch_elem<3, true>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
     }
   } else {
     switch (g.ndof) {
-      case 1: return dispatch_elem<1, false>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
-      case 2: return dispatch_elem<2, false>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
-      case 3: return dispatch_elem<3, false>(mode, g, Ke_host, s, bcmask, bcdiagval, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 1: return dispatch_elem<1, false>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 2: return dispatch_elem<2, false>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
+      case 3: return dispatch_elem<3, false>(mode, g, op, x, b, diag, w, y, dotv, dot_out, ws, st);
     }
   }
   return 1;
 }
 
-// Time every variant of the 3-D matrix-free kernel on the caller's buffers (Jacobi mode, y is scratch) and keep the
-// fastest for this process and this number of dofs per node.  ms_out[pmb_elem_num_variants()] receives the average launch time of each variant.  Not capturable.
-extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const double* s, const unsigned char* bcmask,
-                                 double bcdiagval, const double* x, const double* b, const double* diag, double* y,
-                                 double* ms_out, void* stream) {
+// Time every layout of the 3-D matrix-free kernel on the caller's buffers (Jacobi mode, y is scratch).  ms_out[
+// pmb_elem_num_variants()] receives the average launch time of each layout, *best the fastest one among those whose y is
+// bit-identical to layout 0 (`allow_rounding` != 0 also admits the tensor-core layouts, whose y agrees to rounding).
+// flags_scratch: pmb_elem_autotune_flag_bytes(g) bytes (the brick flags are layout-specific and recomputed per layout;
+// may be NULL when op->bcmask is NULL).  The caller stores *best in its pmb_elem_op.  Not capturable into a CUDA graph.
+extern "C" long long pmb_elem_autotune_flag_bytes(const pmb_grid* p) {
+  const long long a = pmb_elem_brickflags_bytes(p, 4), b = p->ndof == 3 ? pmb_elem_brickflags_bytes(p, 6) : 0;
+  return a > b ? a : b;
+}
+
+extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const double* x, const double* b, const double* diag,
+                                 double* y, unsigned char* flags_scratch, int allow_rounding, double* ms_out, int* best_out,
+                                 void* stream) {
   if (validate_grid(p, "pmb_elem_autotune")) return 1;
   PMB_REQUIRE(p->nz > 0, "pmb_elem_autotune: 3-D grids only");
+  PMB_REQUIRE(op && best_out, "pmb_elem_autotune: NULL pointer argument");
+  PMB_REQUIRE(!op->bcmask || flags_scratch, "pmb_elem_autotune: flags_scratch required with a Dirichlet mask");
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return pmb_set_error("pmb_elem_autotune: cudaEventCreate failed");
-  int& slot = elem_variant(p->ndof);
-  const int saved = slot;
-  int best = saved, rc = 0;
+  pmb_elem_op trial = *op;
+  int best = op->variant, rc = 0;
   float best_ms = 1e30f;
   for (int v = 0; v < PMB_ELEM_VARIANTS && !rc; ++v) {
-    slot = v;
+    trial.variant = v;
+    trial.brickflags = nullptr;
+    const bool wants_flags = (v == 4 || v == 5 || (v == 6 && p->ndof == 3)) && p->ndof != 2;
+    if (op->bcmask && wants_flags) {
+      if (v != 5) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 reuses the flags of 4
+      trial.brickflags = flags_scratch;
+    }
     const int reps = 6;
     for (int r = 0; r < 2 + reps && !rc; ++r) {
       if (r == 2) cudaEventRecord(e0, st);
-      rc = pmb_elem_spmv(p, EMODE_JACOBI, Ke_host, s, bcmask, bcdiagval, x, b, diag, 0.5, y, nullptr, nullptr, nullptr, stream);
+      rc = pmb_elem_spmv(p, EMODE_JACOBI, &trial, x, b, diag, 0.5, y, nullptr, nullptr, nullptr, stream);
     }
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) rc = pmb_set_error("pmb_elem_autotune: %s", cudaGetErrorString(cudaGetLastError()));
@@ -831,11 +1552,11 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const double* Ke_host, const
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= reps;
     if (ms_out) ms_out[v] = ms;
-    // the tensor-core layout is timed and reported but never selected: its y equals the others' only to rounding
-    if (!rc && ms < best_ms && v != 3) best_ms = ms, best = v;
+    const bool rounding = (v == 3 || v == 6) && p->ndof == 3;
+    if (!rc && ms < best_ms && (allow_rounding || !rounding)) best_ms = ms, best = v;
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  slot = rc ? saved : best;
+  *best_out = best;
   return rc;
 }

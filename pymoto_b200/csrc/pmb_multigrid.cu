@@ -359,6 +359,146 @@ extern "C" int pmb_galerkin_rows(const pmb_grid* pf, const pmb_grid* pc, const d
   return 1;
 }
 
+// ------------------------------------------------------------------------------------------------- K6 (direct)
+// Level-1 operator straight from the element densities (host set-up and derivation: pymoto_b200/coarse.py):
+//     Ac = sum_E sum_{p<8} s_child(E,p) G_id(E,p)  [+ the Dirichlet diagonal term, added by pmb_scatter_add]
+// One warp = 32 consecutive coarse nodes of an x-row x ONE neighbour slot (27 warps per CTA): the element / local-node
+// structure is warp-uniform, so the table entry G[id][a][b] is a shared-memory broadcast for unmasked children (id = p)
+// and only coarse elements with a Dirichlet child (cidx >= 0) read per-child ids and the table in global memory.
+// The CTA builds the contiguous run of its 32 nodes in shared memory (same layout as assemble_kernel) and writes it
+// with coalesced stores.  Densities of the 66 x 4 x 4 fine elements around the run are staged once (0.0 outside the grid).
+template <int NDOF>
+__global__ void __launch_bounds__(27 * 32, 1)
+    galerkin_direct_kernel(Geo gf, Geo gc, const double* __restrict__ Gtab, const int* __restrict__ cidx,
+                           const unsigned short* __restrict__ child_ids, const double* __restrict__ s, double* __restrict__ Ac) {
+  constexpr int T = 32, ND2 = NDOF * NDOF, NT = 27 * 32, SW = 2 * T + 2;
+  extern __shared__ double dyn[];
+  double* tile = dyn;                    // T * ND2 * 27 doubles: the output run
+  double* sG = tile + T * ND2 * 27;      // 8 * 64 * ND2: unmasked child tables
+  double* sS = sG + 8 * 64 * ND2;        // 4 x 4 x SW staged densities
+  const int tid = threadIdx.x, gI = tid & 31, slot = tid >> 5;
+  const int I0 = blockIdx.x * T, J = blockIdx.y, kl = blockIdx.z, K = gc.kz0 + kl;
+  const int ni = min(T, gc.NX - I0);
+  for (int p = tid; p < 8 * 64 * ND2; p += NT) sG[p] = Gtab[p];
+  for (int p = tid; p < 16 * SW; p += NT) {
+    const int tx = p % SW, ty = (p / SW) & 3, tz = p / (4 * SW);
+    const int ei = 2 * I0 - 2 + tx, ej = 2 * J - 2 + ty, ek = 2 * K - 2 + tz;
+    // fine layers below the fine slab's two halo layers / above its last owned node plane are never needed
+    const bool in = ei >= 0 && ei < gf.nx && ej >= 0 && ej < gf.ny && ek >= 0 && ek < gf.nzE && ek - gf.kz0 >= -2 &&
+                    ek - gf.kz0 < gf.nzl;
+    sS[p] = in ? __ldg(s + ((long long)(ek - gf.kz0) * gf.ny + ej) * gf.nx + ei) : 0.0;
+  }
+  __syncthreads();
+
+  const int cy = cnt1(J, gc.NY), cz = cnt1(K, gc.NZ);
+  const int Jlo = max(J - 1, 0), Klo = max(K - 1, 0);
+  const long long per = (long long)ND2 * cy * cz;
+  const long long rowbase = pre1(K, gc.NZ) * gc.Sy * gc.Sx + (long long)cz * (pre1(J, gc.NY) * gc.Sx) - gc.bo0;
+  const long long e0 = (long long)ND2 * rowbase + per * pre1(I0, gc.NX);
+  const int nelem = (int)(per * (pre1(I0 + ni, gc.NX) - pre1(I0, gc.NX)));
+
+  const int dk = slot / 9 - 1, dj = (slot / 3) % 3 - 1, di = slot % 3 - 1;   // warp-uniform
+  const int I = I0 + gI, CI = I + di, CJ = J + dj, CK = K + dk;
+  if (gI < ni && CI >= 0 && CI < gc.NX && CJ >= 0 && CJ < gc.NY && CK >= 0 && CK < gc.NZ) {
+    double acc[ND2];
+#pragma unroll
+    for (int q = 0; q < ND2; ++q) acc[q] = 0.0;
+    for (int oz = 0; oz < 2; ++oz) {
+      const int az = 1 - oz, bz = az + dk, EK = K - 1 + oz;
+      if (bz < 0 || bz > 1 || EK < 0 || EK >= gc.nzE) continue;
+      for (int oy = 0; oy < 2; ++oy) {
+        const int ay = 1 - oy, by = ay + dj, EJ = J - 1 + oy;
+        if (by < 0 || by > 1 || EJ < 0 || EJ >= gc.ny) continue;
+        for (int ox = 0; ox < 2; ++ox) {
+          const int ax = 1 - ox, bx = ax + di, EI = I - 1 + ox;
+          if (bx < 0 || bx > 1) continue;        // warp-uniform
+          if (EI < 0 || EI >= gc.nx) continue;   // per lane (first / last node of the row)
+          const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+          const int m = cidx ? __ldg(cidx + ((long long)EK * gc.ny + EJ) * gc.nx + EI) : -1;
+          const double* sp = sS + ((2 * oz) * 4 + 2 * oy) * SW + 2 * (gI + ox);
+          if (m < 0) {
+            const double* gp = sG + (a * 8 + bn) * ND2;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
+#pragma unroll
+              for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, gp[p * 64 * ND2 + q], acc[q]);
+            }
+          } else {
+            const unsigned short* ids = child_ids + 8 * (long long)m;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
+              const double* gp = Gtab + ((long long)__ldg(ids + p) * 64 + a * 8 + bn) * ND2;
+#pragma unroll
+              for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, __ldg(gp + q), acc[q]);
+            }
+          }
+        }
+      }
+    }
+    const int cx = cnt1(I, gc.NX), Ilo = max(I - 1, 0);
+    const int L = cx * cy * cz * NDOF;
+    const int nbr = ((CK - Klo) * cy + (CJ - Jlo)) * cx + (CI - Ilo);
+    double* nodep = tile + per * (pre1(I, gc.NX) - pre1(I0, gc.NX)) + nbr * NDOF;
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) nodep[d * L + c] = acc[d * NDOF + c];
+  }
+  __syncthreads();
+  for (int q = tid; q < nelem; q += NT) Ac[e0 + q] = tile[q];
+}
+
+template <int NDOF>
+static int launch_galerkin_direct(const Geo& gf, const Geo& gc, const double* Gtab, const int* cidx, const unsigned short* child_ids,
+                                  const double* s, double* Ac, cudaStream_t st) {
+  constexpr int T = 32, ND2 = NDOF * NDOF;
+  const size_t smem = sizeof(double) * ((size_t)T * ND2 * 27 + 8 * 64 * ND2 + 16 * (2 * T + 2));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(galerkin_direct_kernel<NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pmb_set_error("galerkin_direct_kernel attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 blocks((gc.NX + T - 1) / T, gc.NY, gc.nzl);
+  galerkin_direct_kernel<NDOF><<<blocks, 27 * 32, smem, st>>>(gf, gc, Gtab, cidx, child_ids, s, Ac);
+  PMB_CHECK_LAUNCH("pmb_galerkin_direct");
+  return 0;
+}
+
+extern "C" int pmb_galerkin_direct(const pmb_grid* pf, const pmb_grid* pc, const double* Gtab, const int* cidx,
+                                   const unsigned short* child_ids, const double* s, double* Ac, void* stream) {
+  if (check_galerkin_grids(pf, pc, "pmb_galerkin_direct")) return 1;
+  PMB_REQUIRE(pf->nz > 0, "pmb_galerkin_direct: 3-D grids only");
+  PMB_REQUIRE(Gtab && s && Ac, "pmb_galerkin_direct: NULL pointer argument");
+  PMB_REQUIRE(!cidx || child_ids, "pmb_galerkin_direct: cidx without child_ids");
+  Geo gf = make_geo(pf), gc = make_geo(pc);
+  PMB_REQUIRE(gc.NY <= 65535 && gc.nzl <= 65535, "pmb_galerkin_direct: grid too large for the 3-D launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (gc.ndof) {
+    case 1: return launch_galerkin_direct<1>(gf, gc, Gtab, cidx, child_ids, s, Ac, st);
+    case 2: return launch_galerkin_direct<2>(gf, gc, Gtab, cidx, child_ids, s, Ac, st);
+    case 3: return launch_galerkin_direct<3>(gf, gc, Gtab, cidx, child_ids, s, Ac, st);
+  }
+  return 1;
+}
+
+// data[idx[i]] += val[i] for unique idx (the constant Dirichlet term of the direct coarse operator)
+__global__ void __launch_bounds__(256) scatter_add_kernel(long long n, const long long* __restrict__ idx, const double* __restrict__ val,
+                                                           double* __restrict__ data) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) data[idx[t]] += val[t];
+}
+
+extern "C" int pmb_scatter_add(long long n, const long long* idx, const double* val, double* data, void* stream) {
+  if (n <= 0) return 0;
+  PMB_REQUIRE(idx && val && data, "pmb_scatter_add: NULL pointer argument");
+  scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, idx, val, data);
+  PMB_CHECK_LAUNCH("pmb_scatter_add");
+  return 0;
+}
+
 extern "C" int pmb_galerkin(const pmb_grid* pf, const pmb_grid* pc, const double* Af, double* Ac, double* work, void* stream) {
   if (pmb_galerkin_cols(pf, pc, Af, work, stream)) return 1;
   return pmb_galerkin_rows(pf, pc, work, Ac, stream);

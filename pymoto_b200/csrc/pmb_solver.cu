@@ -16,8 +16,8 @@ static long long level_rows(const pmb_grid& g) {
 static int level_apply(const pmb_mg_desc* mg, int l, int mode, const double* x, const double* b, double w, double* y,
                        const double* dotv, double* dot_out, double* ws, void* st) {
   const pmb_mg_level& L = mg->level[l];
-  if (l == 0 && mg->Ke_host)
-    return pmb_elem_spmv(&L.grid, mode, mg->Ke_host, mg->s, mg->bcmask, mg->bcdiagval, x, b, L.diag, w, y, dotv, dot_out, ws, st);
+  if (l == 0 && mg->gen.Ke_host)
+    return pmb_elem_spmv(&L.grid, mode, &mg->gen, x, b, L.diag, w, y, dotv, dot_out, ws, st);
   return pmb_spmv(&L.grid, mode, L.A, x, b, L.diag, w, y, dotv, dot_out, ws, st);
 }
 
@@ -58,7 +58,7 @@ static int check_desc(const pmb_mg_desc* mg, const char* who) {
     const pmb_mg_level& L = mg->level[l];
     if (validate_grid(&L.grid, who)) return 1;
     PMB_REQUIRE(L.grid.kz0 == 0 && L.grid.nzl == L.grid.nz + 1, "%s: level %d is a slab (the C driver is single-GPU)", who, l);
-    PMB_REQUIRE((L.A || (l == 0 && mg->Ke_host)) && L.diag && L.u && L.u2 && L.t && L.rc, "%s: NULL pointer in level %d", who, l);
+    PMB_REQUIRE((L.A || (l == 0 && mg->gen.Ke_host)) && L.diag && L.u && L.u2 && L.t && L.rc, "%s: NULL pointer in level %d", who, l);
     PMB_REQUIRE(L.smooth_steps >= 1 && L.w > 0.0 && L.w <= 1.0, "%s: level %d smoother (steps %d, w %g)", who, l, L.smooth_steps, L.w);
     const pmb_grid& c = (l + 1 < mg->nlevels) ? mg->level[l + 1].grid : mg->coarse_grid;
     PMB_REQUIRE(L.grid.nx == 2 * c.nx && L.grid.ny == 2 * c.ny && L.grid.nz == 2 * c.nz && L.grid.ndof == c.ndof,
@@ -66,7 +66,7 @@ static int check_desc(const pmb_mg_desc* mg, const char* who) {
   }
   if (validate_grid(&mg->coarse_grid, who)) return 1;
   PMB_REQUIRE(mg->coarse_inv && mg->coarse_out, "%s: coarsest-level inverse / output missing", who);
-  PMB_REQUIRE(!mg->Ke_host || mg->s, "%s: generator without element scaling vector", who);
+  PMB_REQUIRE(!mg->gen.Ke_host || mg->gen.s, "%s: generator without element scaling vector", who);
   return 0;
 }
 

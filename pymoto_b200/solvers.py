@@ -156,6 +156,10 @@ class GeometricMultigrid(Preconditioner):
     # a single GPU.  Every buffer the cycle touches is persistent, so the graph is captured once per hierarchy and only
     # re-captured if an address changes.  PMB_CUDA_GRAPH=0 disables it.
     use_cuda_graph = os.environ.get("PMB_CUDA_GRAPH", "1") != "0"
+    # Build the level-1 operator straight from the element densities (pmb_galerkin_direct, pymoto_b200/coarse.py) when the
+    # fine matrix comes from an assembly module (3-D): the fine values are not read and no intermediate is written.
+    # PMB_GALERKIN_DIRECT=0 keeps the generic two-pass product R^T (A R) on every level.
+    direct_level1 = os.environ.get("PMB_GALERKIN_DIRECT", "1") != "0"
 
     def __init__(self, domain, A=None, cycle: str = "V", inner_level: LinearSolver = None, smoother: LinearSolver = None,
                  smooth_steps: int = 5):
@@ -192,22 +196,46 @@ class GeometricMultigrid(Preconditioner):
             self._fine_key = (g.kz0, g.nzl, A.comm is not None)
             self._setup_coarse(A)
         gcl = self._gc_local
-        # two streaming passes; between them the lower halo plane of the column-collapsed intermediate is fetched
-        # from the rank below (its top owned fine plane contributes to my first coarse plane)
-        nwork = _lib.query("pmb_galerkin_ws_doubles", g)
-        bplane = nwork // g.nzl  # one node plane of the intermediate
-        work = dv.workspace().galerkin_ws(nwork + bplane)
         st = dv.stream()
-        _lib.call("pmb_galerkin_cols", g, gcl, dv.ptr(A._buf), work.data_ptr() + 8 * bplane, st)
-        if A.comm is not None:
-            A.comm.exchange(work, bplane, nwork, bplane, lower=True, upper=False)
-        _lib.call("pmb_galerkin_rows", g, gcl, work.data_ptr() + 8 * bplane, dv.ptr(self._Ac_local._buf), st)
+        gen = A.generator
+        if GeometricMultigrid.direct_level1 and A.level == 0 and gen is not None and g.nz > 0:
+            t = self._direct_tables(gen, gcl)
+            _lib.call("pmb_galerkin_direct", g, gcl, dv.ptr(t["Gtab"]), dv.ptr(t["cidx"]), dv.ptr(t["child_ids"]), gen.s.data_ptr(),
+                      dv.ptr(self._Ac_local._buf), st)
+            if t["bc_idx"] is not None:
+                _lib.call("pmb_scatter_add", t["bc_idx"].numel(), dv.ptr(t["bc_idx"]), dv.ptr(t["bc_val"]), dv.ptr(self._Ac_local._buf), st)
+        else:
+            # two streaming passes; between them the lower halo plane of the column-collapsed intermediate is fetched
+            # from the rank below (its top owned fine plane contributes to my first coarse plane)
+            nwork = _lib.query("pmb_galerkin_ws_doubles", g)
+            bplane = nwork // g.nzl  # one node plane of the intermediate
+            work = dv.workspace().galerkin_ws(nwork + bplane)
+            _lib.call("pmb_galerkin_cols", g, gcl, dv.ptr(A._buf), work.data_ptr() + 8 * bplane, st)
+            if A.comm is not None:
+                A.comm.exchange(work, bplane, nwork, bplane, lower=True, upper=False)
+            _lib.call("pmb_galerkin_rows", g, gcl, work.data_ptr() + 8 * bplane, dv.ptr(self._Ac_local._buf), st)
         if self._replicate:  # first replicated level: every rank gets the whole coarse operator
             A.comm.gather_full(self._Ac_local.data, self.Ac.data, self._coarse_entry_offset)
         self.Ac.invalidate()
         if self.inner_level is None:
             self.inner_level = SolverDenseInverse()
         self.inner_level.update(self.Ac)
+
+    def _direct_tables(self, gen, gcl):
+        """Device copies of the constant tables of the direct level-1 build (once per element matrix / bc set / slab)."""
+        from . import coarse
+
+        key = (id(gen), gen.ke.tobytes(), gen.bcdiag, gcl.kz0, gcl.nzl)
+        if getattr(self, "_direct_key", None) != key:
+            g = gen.grid
+            h = coarse.build_tables(gen.ke, g.ndof, (g.nx, g.ny, g.nz), gen.bc if gen.mask is not None else None, gen.bcdiag,
+                                    gcl.kz0, gcl.kz0 + gcl.nzl)
+            up = lambda a, dt: None if a is None or a.size == 0 else dv.to_device(a, dt)  # noqa: E731
+            self._direct = dict(Gtab=dv.to_device(h["Gtab"].ravel()), cidx=up(h["cidx"], torch.int32),
+                                child_ids=None if h["child_ids"] is None else dv.to_device(np.ascontiguousarray(h["child_ids"]).view(np.int16).ravel(), torch.int16),
+                                bc_idx=up(h["bc_idx"], torch.int64), bc_val=up(h["bc_val"], torch.float64))
+            self._direct_key = key
+        return self._direct
 
     def _setup_coarse(self, A):
         """Coarse operator storage and level buffers (once per problem)."""
@@ -246,7 +274,7 @@ class GeometricMultigrid(Preconditioner):
             gen = lvl.A.generator if DeviceCSR.matrix_free else None
             sig += [lvl.A._buf.data_ptr(), lvl.smoother.D.data_ptr(), float(lvl.smoother.w), lvl.smooth_steps,
                     None if gen is None else (gen["s"].data_ptr(), None if gen["mask"] is None else gen["mask"].data_ptr(),
-                                              gen["bcdiag"], gen["ke"].ctypes.data, gen["ke"].tobytes())]
+                                              gen["bcdiag"], gen["ke"].ctypes.data, gen["ke"].tobytes(), gen.variant)]
             sig += [lvl._buf[k].data_ptr() for k in ("u", "u2", "t", "rc")]
             lvl = lvl.inner_level
         if not isinstance(lvl, SolverDenseInverse) or lvl.inv is None:
@@ -401,9 +429,7 @@ class CG(LinearSolver):
         desc.coarse_inv, desc.coarse_out = lvl.inv.data_ptr(), lvl._out.data_ptr()
         gen = A.generator if DeviceCSR.matrix_free else None
         if gen is not None:
-            desc.Ke_host, desc.s = gen["ke"].ctypes.data, gen["s"].data_ptr()
-            desc.bcmask = None if gen["mask"] is None else gen["mask"].data_ptr()
-            desc.bcdiagval = float(gen["bcdiag"])
+            desc.gen = gen.op()
         self._desc_keep = (keep, gen)
         return desc
 

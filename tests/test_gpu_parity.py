@@ -162,6 +162,43 @@ def test_transfer_and_galerkin_vs_golden(pmb):
         np.testing.assert_allclose(Ac.data, ref, rtol=1e-12, atol=1e-13 * np.abs(ref).max())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ndof,nbc", [((6, 4, 4), 3, 11), ((10, 6, 8), 3, 40), ((66, 4, 4), 3, 25), ((8, 8, 8), 1, 9), ((12, 6, 4), 3, 0),
+                                            ((70, 6, 6), 1, 30)])
+def test_galerkin_direct_vs_scipy(pmb, shape, ndof, nbc):
+    """pmb_galerkin_direct (level 1 straight from the element densities, Dirichlet patterns through the table lookup, the
+    bc diagonal term through pmb_scatter_add) against scipy's R^T K R with the oracle's prolongation matrix, and against
+    the generic two-pass product of the same operator: values rtol 1e-12 (of the largest entry for cancelling ones)."""
+    from oracle.solvers import prolongation_matrix
+    from pymoto_b200.solvers import GeometricMultigrid
+
+    rng = np.random.default_rng(11)
+    gr, gc = Grid(*shape), Grid(*(v // 2 for v in shape))
+    dom = pmb.VoxelDomain(*shape)
+    Ke = rng.standard_normal((8 * ndof,) * 2)
+    Ke = Ke + Ke.T + 8 * np.eye(Ke.shape[0])
+    bc = np.unique(rng.integers(0, gr.nnodes * ndof, nbc)) if nbc else None
+    if nbc == 40:  # a fully clamped face as well (the cantilever pattern)
+        bc = np.unique(np.concatenate([bc, (gr.nodes3d()[0, :, :].ravel()[:, None] * ndof + np.arange(ndof)).ravel()]))
+    K = pmb.AssembleGeneral(dom, Ke, bc=bc)(rng.random(gr.nel))
+    R = prolongation_matrix(gr, gc, ndof)
+    ref = (R.T @ K.tocsr() @ R).tocsr()
+    ref.sort_indices()
+    assert GeometricMultigrid.direct_level1
+    mg = GeometricMultigrid(dom)
+    mg.update(K)
+    Ad = mg.Ac.tocsr()
+    assert np.array_equal(Ad.indptr, ref.indptr) and np.array_equal(Ad.indices, ref.indices)
+    np.testing.assert_allclose(Ad.data, ref.data, rtol=1e-12, atol=1e-13 * np.abs(ref.data).max())
+    try:
+        GeometricMultigrid.direct_level1 = False
+        mg2 = GeometricMultigrid(dom)
+        mg2.update(K)
+        np.testing.assert_allclose(mg2.Ac.data.cpu().numpy(), Ad.data, rtol=1e-12, atol=1e-13 * np.abs(ref.data).max())
+    finally:
+        GeometricMultigrid.direct_level1 = True
+
+
 def test_restriction_constants(pmb):
     """reference tests/test_solvers_multigrid.py:9-91 on the kernels: restriction of ones = 8/6/4.5/3.375 (3-D)."""
     from pymoto_b200 import _lib, device as dv
@@ -454,14 +491,16 @@ def test_matrix_free_operator_equals_assembled(pmb, shape, ndof):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3), ((5, 20, 19), 3), ((34, 9, 17), 2)])
+@pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3), ((5, 20, 19), 3), ((34, 9, 17), 2),
+                                        ((66, 16, 5), 3), ((31, 8, 2), 3)])
 def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     """Every layout of the 3-D matrix-free kernel must reproduce variant 0 (one node per thread on a brick): the z-marching
-    columns (1, 2) bit for bit, the FP64 tensor-core layout (3; DMMA accumulation order) to 1e-11 of the field magnitude in y (same products, same order per node) for all modes, on the whole grid and
+    columns (1, 2) and the bulk-copy ring layouts (4, 5; with and without brick flags) bit for bit, the FP64 tensor-core layout (3; DMMA accumulation order) to 1e-11 of the field magnitude in y (same products, same order per node) for all modes, on the whole grid and
     on sub-slabs with odd plane counts; the fused dot products agree to rounding.  The autotune entry point runs, returns
     one time per variant and leaves a valid selection."""
     import ctypes as C
 
+    import torch
     from pymoto_b200 import _lib, device as dv
     from pymoto_b200.matrix import make_grid
 
@@ -475,19 +514,19 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     n = K.shape[0]
     vd, bd = dv.to_device(rng.standard_normal(n)), dv.to_device(rng.standard_normal(n))
     D = K.diagonal_device()
-    saved = _lib.query("pmb_elem_get_variant", ndof)
+    gen = K.generator
+    saved = gen.variant
     try:
         ref = {}
         nvar = _lib.query("pmb_elem_num_variants")
-        assert nvar >= 4
+        assert nvar >= 7
         for variant in range(nvar):
-            _lib.call("pmb_elem_set_variant", variant)
-            assert _lib.query("pmb_elem_get_variant", ndof) == variant
+            gen.variant = variant
             for mode in (_lib.SPMV, _lib.RESIDUAL, _lib.JACOBI):
                 out, d3 = dv.zeros(n), dv.empty(3)
                 K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
                 got = (out.cpu().numpy(), d3.cpu().numpy())
-                exact = variant in (1, 2) or ndof != 3
+                exact = variant not in (3, 6) or ndof != 3
                 if variant == 0:
                     ref[mode] = got
                 elif exact:
@@ -499,11 +538,10 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
             # a sub-slab [k0, k0 + 3) of the same operator: pointers move with the slab, halo planes are read around it
             g, k0, npl = K.grid, 1, 3
             sg = make_grid(g.nx, g.ny, g.nz, g.ndof, k0, npl)
-            plane, lay = K.plane, g.nx * g.ny
-            gen = K.generator
+            plane = K.plane
             out = dv.zeros(n)
-            _lib.call("pmb_elem_spmv", sg, _lib.JACOBI, gen["ke"].ctypes.data, gen["s"].data_ptr() + 8 * k0 * lay,
-                      gen["mask"].data_ptr() + k0 * plane, float(gen["bcdiag"]), vd.data_ptr() + 8 * k0 * plane,
+            xin = K._padded(vd)
+            _lib.call("pmb_elem_spmv", sg, _lib.JACOBI, C.byref(gen.op(sg, k0)), xin.data_ptr() + 8 * k0 * plane,
                       bd.data_ptr() + 8 * k0 * plane, D.data_ptr() + 8 * k0 * plane, 0.5, out.data_ptr() + 8 * k0 * plane,
                       None, None, None, dv.stream())
             got = out.cpu().numpy()
@@ -513,15 +551,29 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
                 assert np.array_equal(got, want), ("slab", variant)
             else:
                 np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * max(1.0, np.abs(want).max()))
+            if variant in (4, 5, 6):  # without brick flags every brick applies the mask: same result
+                op = gen.op()
+                bare = _lib.ElemOp(op.Ke_host, op.s, op.bcmask, op.bcdiagval, None, variant)
+                out = dv.zeros(n)
+                _lib.call("pmb_elem_spmv", K.grid, _lib.JACOBI, C.byref(bare), xin.data_ptr(), bd.data_ptr(), D.data_ptr(), 0.5,
+                          out.data_ptr(), None, None, None, dv.stream())
+                if exact:
+                    assert np.array_equal(out.cpu().numpy(), ref[_lib.JACOBI][0]), ("no flags", variant)
+                else:
+                    np.testing.assert_allclose(out.cpu().numpy(), ref[_lib.JACOBI][0], rtol=0, atol=1e-11 * max(1.0, np.abs(ref[_lib.JACOBI][0]).max()))
         ms = (C.c_double * nvar)()
+        best = C.c_int(-1)
         scratch = dv.zeros(n)
-        _lib.call("pmb_elem_autotune", K.grid, gen["ke"].ctypes.data, gen["s"].data_ptr(), gen["mask"].data_ptr(),
-                  float(gen["bcdiag"]), vd.data_ptr(), bd.data_ptr(), D.data_ptr(), scratch.data_ptr(), C.addressof(ms), dv.stream())
-        assert all(0.0 < t < 1e3 for t in ms)
-        assert 0 <= _lib.query("pmb_elem_get_variant", ndof) < nvar
+        fscr = dv.empty(_lib.query("pmb_elem_autotune_flag_bytes", K.grid), torch.uint8)
+        for allow in (1, 0):
+            _lib.call("pmb_elem_autotune", K.grid, C.byref(gen.op()), xin.data_ptr(), bd.data_ptr(), D.data_ptr(), scratch.data_ptr(),
+                      fscr.data_ptr(), allow, C.addressof(ms), C.byref(best), dv.stream())
+            assert all(0.0 < t < 1e3 for t in ms)
+            assert 0 <= best.value < nvar
+        assert best.value not in (3, 6) or ndof != 3
         np.testing.assert_allclose(scratch.cpu().numpy(), ref[_lib.JACOBI][0], rtol=0, atol=1e-11 * max(1.0, np.abs(ref[_lib.JACOBI][0]).max()))
     finally:
-        _lib.call("pmb_elem_set_variant", saved)
+        gen.variant = saved
 
 
 # ------------------------------------------------------------------------------------------------ FilterConv (next row f1)

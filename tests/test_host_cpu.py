@@ -212,10 +212,10 @@ def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
 #define S(t) printf(#t " %zu\n", sizeof(t))
 #define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
 int main(void) {
-  S(pmb_grid); S(pmb_coef); S(pmb_bound); S(pmb_mma_vecs); S(pmb_mg_level); S(pmb_mg_desc);
+  S(pmb_grid); S(pmb_coef); S(pmb_bound); S(pmb_mma_vecs); S(pmb_mg_level); S(pmb_mg_desc); S(pmb_elem_op);
   O(pmb_coef, sqrt_den); O(pmb_bound, v); O(pmb_mma_vecs, Q); O(pmb_mg_level, A); O(pmb_mg_level, smooth_steps);
-  O(pmb_mg_level, w); O(pmb_mg_desc, level); O(pmb_mg_desc, coarse_grid); O(pmb_mg_desc, coarse_inv); O(pmb_mg_desc, Ke_host);
-  O(pmb_mg_desc, bcdiagval);
+  O(pmb_mg_level, w); O(pmb_mg_desc, level); O(pmb_mg_desc, coarse_grid); O(pmb_mg_desc, coarse_inv); O(pmb_mg_desc, gen);
+  O(pmb_elem_op, bcdiagval); O(pmb_elem_op, brickflags); O(pmb_elem_op, variant);
   printf("PMB_MMA_MAXM %d\nPMB_MAX_LEVELS %d\n", PMB_MMA_MAXM, PMB_MAX_LEVELS);
   return 0;
 }
@@ -224,7 +224,7 @@ int main(void) {
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     mirrors = {"pmb_grid": _lib.Grid, "pmb_coef": _lib.Coef, "pmb_bound": _lib.Bound, "pmb_mma_vecs": _lib.MmaVecs,
-               "pmb_mg_level": _lib.MgLevel, "pmb_mg_desc": _lib.MgDesc}
+               "pmb_mg_level": _lib.MgLevel, "pmb_mg_desc": _lib.MgDesc, "pmb_elem_op": _lib.ElemOp}
     for name, cls in mirrors.items():
         assert int(got[name]) == ctypes.sizeof(cls), (name, got[name], ctypes.sizeof(cls))
     for key, val in got.items():
@@ -232,3 +232,37 @@ int main(void) {
             st, field = key.split(".")
             assert int(val) == getattr(mirrors[st], field).offset, (key, val)
     assert int(got["PMB_MMA_MAXM"]) == _lib.MMA_MAXM and int(got["PMB_MAX_LEVELS"]) == _lib.MAX_LEVELS
+
+
+def test_direct_coarse_operator_tables_vs_oracle():
+    """Host set-up of the direct level-1 Galerkin build (pymoto_b200/coarse.py): eight child tables, Dirichlet-pattern
+    tables, per-coarse-element lookup and the bc diagonal term, evaluated in plain numpy, equal the oracle's R^T A R --
+    whole grid and as coarse slabs (multi-GPU row ranges)."""
+    import scipy.sparse as sps
+
+    import oracle.assembly as oasm
+    import oracle.solvers as osol
+    from oracle import Grid
+    from pymoto_b200 import coarse
+
+    rng = np.random.default_rng(0)
+    for dims, ndof in [((4, 4, 4), 3), ((6, 4, 4), 1)]:
+        g, gc = Grid(*dims), Grid(*(d // 2 for d in dims))
+        Ke = rng.standard_normal((8 * ndof,) * 2)
+        Ke = Ke + Ke.T + 8 * np.eye(8 * ndof)
+        bc = np.unique(rng.integers(0, g.nnodes * ndof, 9))
+        asm = oasm.Assembler(g, Ke, bc=bc)
+        s = rng.random(g.nel)
+        R = osol.prolongation_matrix(g, gc, ndof)
+        ref = (R.T @ asm(s) @ R).tocsr()
+        ref.sort_indices()
+        tabs = coarse.build_tables(Ke, ndof, dims, bc, asm.bcdiagval)
+        assert tabs["Gtab"].shape[0] > 8 and tabs["cidx"].max() >= 0
+        data = coarse.emulate(tabs, ndof, dims, s)
+        ip, ix = oasm.pattern_closed_form(gc, ndof)
+        mine = sps.csr_matrix((data, ix, ip), shape=ref.shape)
+        assert abs(mine - ref).max() <= 1e-13 * abs(ref).max()
+        plane = (gc.nelx + 1) * (gc.nely + 1) * ndof
+        for k0c, k1c in [(0, 1), (1, dims[2] // 2 + 1)]:
+            t2 = coarse.build_tables(Ke, ndof, dims, bc, asm.bcdiagval, k0c, k1c)
+            assert np.array_equal(coarse.emulate(t2, ndof, dims, s, k0c, k1c), data[ip[k0c * plane]:ip[k1c * plane]])
