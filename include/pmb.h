@@ -82,9 +82,10 @@ int pmb_csr_pattern(const pmb_grid* g, void* indptr, void* indices, int index_bi
 /* K1: data = sum_e x_e Ke (sequential adds from 0.0 in ascending element number, no FMA: bit-exact with
  * np.add.at), rows/cols in bcmask (1 byte per dof, may be NULL) zeroed, bc diagonal = bcdiagval.
  * x points at element layer kz0 (layer kz0-1 is read as halo when kz0 > 0). Ke is (nn*ndof)^2 row-major and a HOST
- * pointer (it is passed to the kernel through the parameter constant bank). */
+ * pointer (it is passed to the kernel through the parameter constant bank).  diag / nnz_offdiag (either may be NULL): the
+ * row statistics of pmb_rowstats, produced while the rows are still on chip (no second pass over the values in 3-D). */
 int pmb_assemble(const pmb_grid* g, const double* Ke_host, const double* x, const unsigned char* bcmask,
-                 double bcdiagval, double* data, void* stream);
+                 double bcdiagval, double* data, double* diag, int* nnz_offdiag, void* stream);
 
 /* K11: dx_e = sum_{a,b} u[dof(e,a)] Ke[a,b] v[dof(e,b)], u and v taken as 0 at masked dofs.
  * Element layers [kz0, min(kz0+nzl, nz)) are produced (all elements in 2-D). accumulate != 0 adds into dx. */
@@ -227,6 +228,22 @@ int pmb_vec_div(long long n, const double* a, const double* b, double* out, void
 /* Multi-GPU halo mailboxes: two independent n-double copies in one launch (dst may be PEER memory mapped through
  * symmetric memory: the stores then travel over NVLink).  Any (src, dst) pair with a NULL member is skipped. */
 int pmb_halo_copy2(long long n, const double* src0, double* dst0, const double* src1, double* dst1, void* stream);
+
+/* ---- slab communication over NCCL: lets a host without torch.distributed drive the z-slab path.  NCCL is
+ * bound at run time (dlopen libnccl.so.2); without it these return an error.  One handle per process / GPU, made from a
+ * 128-byte ncclUniqueId that rank 0 creates (pmb_comm_unique_id) and the caller distributes.  z-neighbours are rank +- 1.
+ * pmb_halo_exchange: base[own_offset, own_offset + own_len) are the owned doubles of a padded device buffer, the n doubles
+ * below / above are halos; lower / upper select which of MY halos are refilled (all ranks pass the same flags).
+ * pmb_allreduce: in-place sum of `count` device doubles (dot products, compliance, volume). */
+typedef struct pmb_comm pmb_comm;
+int pmb_comm_unique_id(void* id128);
+int pmb_comm_init(const void* id128, int rank, int nranks, pmb_comm** out);
+int pmb_comm_destroy(pmb_comm* c);
+int pmb_comm_rank(const pmb_comm* c);
+int pmb_comm_size(const pmb_comm* c);
+int pmb_halo_exchange(pmb_comm* c, double* base, long long own_offset, long long own_len, long long n, int lower, int upper,
+                      void* stream);
+int pmb_allreduce(pmb_comm* c, double* buf, long long count, void* stream);
 
 /* OC update, one bisection candidate (pymoto/common/optimizers.py:425-435): xnew = clip(x sqrt(-min(dg,0)/lmid),
  * max(xmin, x-move), min(xmax, x+move)), sum_out = sum(xnew) (deterministic). xnew may be NULL. ws: pmb_ws_doubles(). */

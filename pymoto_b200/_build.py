@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpmb.so")
-SOURCES = ["pmb_api.cu", "pmb_assembly.cu", "pmb_spmv.cu", "pmb_multigrid.cu", "pmb_vector.cu", "pmb_filter.cu", "pmb_elem.cu", "pmb_optim.cu", "pmb_solver.cu", "pmb_probe.cu"]
+SOURCES = ["pmb_api.cu", "pmb_assembly.cu", "pmb_spmv.cu", "pmb_multigrid.cu", "pmb_vector.cu", "pmb_filter.cu", "pmb_elem.cu", "pmb_optim.cu", "pmb_solver.cu", "pmb_probe.cu", "pmb_comm.cu"]
 
 
 def needs_build():
@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
     cmd += ["-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-cudart", "shared"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -83,7 +83,7 @@ SIGNATURES = {
     "pmb_nnz": (_LL, [_G]),
     "pmb_nrows": (_LL, [_G]),
     "pmb_csr_pattern": (_I, [_G, _P, _P, _I, _P]),
-    "pmb_assemble": (_I, [_G, _P, _P, _P, _D, _P, _P]),
+    "pmb_assemble": (_I, [_G, _P, _P, _P, _D, _P, _P, _P, _P]),
     "pmb_assemble_sens": (_I, [_G, _P, _P, _P, _P, _P, _I, _P]),
     "pmb_rowstats": (_I, [_G, _P, _P, _P, _P]),
     "pmb_spmv": (_I, [_G, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
@@ -121,6 +121,13 @@ SIGNATURES = {
     "pmb_stencil_corr": (_I, [_I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_halo_copy2": (_I, [_LL, _P, _P, _P, _P, _P]),
+    "pmb_comm_unique_id": (_I, [_P]),
+    "pmb_comm_init": (_I, [_P, _I, _I, C.POINTER(C.c_void_p)]),
+    "pmb_comm_destroy": (_I, [_P]),
+    "pmb_comm_rank": (_I, [_P]),
+    "pmb_comm_size": (_I, [_P]),
+    "pmb_halo_exchange": (_I, [_P, _P, _LL, _LL, _LL, _I, _I, _P]),
+    "pmb_allreduce": (_I, [_P, _P, _LL, _P]),
     "pmb_oc_candidate": (_I, [_LL, _P, _P, _D, _D, _D, _D, _P, _P, _P, _P]),
     "pmb_mma_ws_doubles": (_LL, []),
     "pmb_mma_asymptotes": (_I, [_LL, _P, _P, _P, _D, _D, _D, _P, _P]),
@@ -157,6 +164,8 @@ def _kernels_launched(name, args):
         return 8 * load().pmb_elem_num_variants()  # every variant: 2 warm-up + 6 timed launches
     if name == "pmb_probe_fp64":
         return 4
+    if name.startswith("pmb_comm_") or name in ("pmb_halo_exchange", "pmb_allreduce"):
+        return 0  # NCCL's own kernels
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":

@@ -147,9 +147,12 @@ class AssembleGeneral(Module):
         if self._mat is None:
             self._mat = DeviceCSR(self.grid, bc_mask=self._bcmask, comm=self._ctx.comm, level=0)
         mat = self._mat
+        diag, nnz_off = mat.rowstats_buffers()  # filled by the assembly kernel while the rows are on chip
         _lib.call("pmb_assemble", self.grid, self._Ke_host.ctypes.data, dv.ptr(x), dv.ptr(self._bcmask),
-                  float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.stream())
+                  float(self.bcdiagval if self.bcdiagval is not None else 0.0), dv.ptr(mat._buf), dv.ptr(diag), dv.ptr(nnz_off),
+                  dv.stream())
         mat.invalidate()
+        mat._diag, mat._nnz_off = diag, nnz_off
         if mat.generator is None:
             mat.generator = ElemGenerator(self.grid, self._Ke_host, x, self._bcmask,
                                           float(self.bcdiagval if self.bcdiagval is not None else 0.0), bc=self.bc)

@@ -5,6 +5,7 @@
 // The scatter of the reference is turned into a gather: one thread owns one (row, neighbour-node) slot and
 // sums the <= 8 (4 in 2-D) element contributions in ascending element number with a separate multiply and add
 // (no FMA), which is the order and rounding of the sequential np.add.at loop -> values are bit-identical.
+#include <cstdlib>
 #include "pmb_common.cuh"
 
 // ------------------------------------------------------------------------------------------------- K0
@@ -170,11 +171,124 @@ if (!DIM3 || part == 1) assemble_node_plane<NDOF, DIM3, 0>(g, ke, x, bcmask, bcd
   for (int q = tid; q < nelem; q += NT) data[e0 + q] = tile[q];
 }
 
+// 3-D layout with one WARP per (32 nodes of an x-row, neighbour line): 9 warps per CTA, each taking the three slots
+// (di = -1, 0, 1) of one (dk, dj) line in turn, 3 CTAs per SM so that the compute phase of one CTA overlaps the write-out of
+// another.  assemble_kernel above keeps 3 threads per node and 62 KB of shared memory per 96-thread CTA (9 resident warps per
+// SM: instruction-issue bound at 0.36 of the HBM write rate); here the line -- hence the element / local-node structure and
+// every Ke index -- is warp-uniform and a thread owns one NDOF x NDOF block at a time.  Same arithmetic: per entry the
+// element terms in ascending element number with separate multiply and add -> the same bits as np.add.at.
+template <int NDOF>
+__global__ void __launch_bounds__(9 * 32, 3) assemble_slot_kernel(Geo g, const __grid_constant__ AsmKe<NDOF, true> ke,
+                                                                   const double* __restrict__ x,
+                                                                   const unsigned char* __restrict__ bcmask, double bcdiagval,
+                                                                   double* __restrict__ data, double* __restrict__ diag_out,
+                                                                   int* __restrict__ nnz_out) {
+  constexpr int T = 32, ND2 = NDOF * NDOF, LD = 8 * NDOF, NT = 9 * 32;
+  extern __shared__ double tile[];  // T * ND2 * 27 doubles, then the element matrix
+  double* sKe = tile + T * ND2 * 27;
+  const int tid = threadIdx.x, gI = tid & 31, line = tid >> 5;
+  const int i0 = blockIdx.x * T, j = blockIdx.y, kl = blockIdx.z, k = g.kz0 + kl;
+  const int ni = min(T, g.NX - i0);
+  for (int q = tid; q < LD * LD; q += NT) sKe[q] = ke.v[q];
+  __syncthreads();
+  const int cy = cnt1(j, g.NY), cz = cnt1(k, g.NZ);
+  const int jlo = max(j - 1, 0), klo = max(k - 1, 0);
+  const long long per = (long long)ND2 * cy * cz;
+  const long long rowbase = pre1(k, g.NZ) * g.Sy * g.Sx + (long long)cz * (pre1(j, g.NY) * g.Sx) - g.bo0;
+  const long long e0 = (long long)ND2 * rowbase + per * pre1(i0, g.NX);
+  const int nelem = (int)(per * (pre1(i0 + ni, g.NX) - pre1(i0, g.NX)));
+  const int dk = line / 3 - 1, dj = line % 3 - 1;   // warp-uniform
+  const int i = i0 + gI, cj = j + dj, ck = k + dk;
+  if (gI < ni && cj >= 0 && cj < g.NY && ck >= 0 && ck < g.NZ) {
+    const long long ln = ((long long)kl * g.NY + j) * g.NX + i;
+    const int cx = cnt1(i, g.NX), ilo = max(i - 1, 0);
+    const int L = cx * cy * cz * NDOF;
+    bool rowbc[NDOF];
+#pragma unroll
+    for (int d = 0; d < NDOF; ++d) rowbc[d] = bcmask && bcmask[ln * NDOF + d];
+    // densities of the (up to) 4 elements of this line around the node: (i-1+ox, j-1+oy, k-1+oz) with oy / oz fixed by
+    // dj / dk when they are non-zero
+#pragma unroll
+    for (int di = -1; di <= 1; ++di) {
+      const int ci = i + di;
+      if (ci < 0 || ci >= g.NX) continue;
+      double acc[ND2];
+#pragma unroll
+      for (int q = 0; q < ND2; ++q) acc[q] = 0.0;
+      for (int oz = 0; oz < 2; ++oz) {      // elements in ascending number
+        const int az = 1 - oz, bz = az + dk, ek = k - 1 + oz;
+        if (bz < 0 || bz > 1 || ek < 0 || ek >= g.nzE) continue;
+        for (int oy = 0; oy < 2; ++oy) {
+          const int ay = 1 - oy, by = ay + dj, ej = j - 1 + oy;
+          if (by < 0 || by > 1 || ej < 0 || ej >= g.ny) continue;
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) {
+            const int ax = 1 - ox, bx = ax + di, ei = i - 1 + ox;
+            if (bx < 0 || bx > 1) continue;       // compile-time
+            if (ei < 0 || ei >= g.nx) continue;   // per lane
+            const double xe = __ldg(x + ((long long)(ek - g.kz0) * g.ny + ej) * g.nx + ei);
+            const double* kp = sKe + ((ax + 2 * ay + 4 * az) * NDOF) * LD + (bx + 2 * by + 4 * bz) * NDOF;
+#pragma unroll
+            for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+              for (int c = 0; c < NDOF; ++c) acc[d * NDOF + c] = __dadd_rn(acc[d * NDOF + c], __dmul_rn(kp[d * LD + c], xe));
+          }
+        }
+      }
+      const long long lc = ((long long)(ck - g.kz0) * g.NY + cj) * g.NX + ci;   // may lie in a halo plane
+      const bool self = dk == 0 && dj == 0 && di == 0;
+      const int nbr = ((ck - klo) * cy + (cj - jlo)) * cx + (ci - ilo);
+      double* nodep = tile + per * (pre1(i, g.NX) - pre1(i0, g.NX)) + nbr * NDOF;
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) {
+          const bool colbc = bcmask && bcmask[lc * NDOF + c];
+          nodep[d * L + c] = (rowbc[d] || colbc) ? ((self && c == d) ? bcdiagval : 0.0) : acc[d * NDOF + c];
+        }
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < nelem; q += NT) data[e0 + q] = tile[q];
+  // row statistics while the rows are on chip (what pmb_rowstats would re-read 8 bytes per non-zero for): diagonal entry
+  // and number of non-zero off-diagonals of every row of the run
+  if ((diag_out || nnz_out) && tid < ni * NDOF) {
+    const int gi = tid / NDOF, d = tid - gi * NDOF, ii = i0 + gi;
+    const int cx = cnt1(ii, g.NX), ilo = max(ii - 1, 0);
+    const int L = cx * cy * cz * NDOF;
+    const double* row = tile + per * (pre1(ii, g.NX) - pre1(i0, g.NX)) + d * L;
+    const int self = (((k - klo) * cy + (j - jlo)) * cx + (ii - ilo)) * NDOF + d;
+    int cnt = 0;
+    for (int q = 0; q < L; ++q) cnt += (q != self && row[q] != 0.0) ? 1 : 0;
+    const long long r = (((long long)kl * g.NY + j) * g.NX + ii) * NDOF + d;
+    if (diag_out) diag_out[r] = row[self];
+    if (nnz_out) nnz_out[r] = cnt;
+  }
+}
+
 template <int NDOF, bool DIM3>
 static int launch_assemble(const Geo& g, const double* Ke_host, const double* x, const unsigned char* bcmask, double bcdiagval,
-                           double* data, cudaStream_t st) {
+                           double* data, double* diag, int* nnz_offdiag, bool* stats_done, cudaStream_t st) {
   AsmKe<NDOF, DIM3> ke;
   memcpy(ke.v, Ke_host, sizeof(ke.v));
+  if constexpr (DIM3) {
+    constexpr int T = 32, LD = 8 * NDOF;
+    const size_t smem = sizeof(double) * (T * NDOF * NDOF * 27 + LD * LD);
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(assemble_slot_kernel<NDOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return pmb_set_error("assemble_slot_kernel attribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    static const bool legacy = getenv("PMB_ASSEMBLE_LEGACY") != nullptr;  // the 3-threads-per-node kernel, for A/B timing
+    if (!legacy) {
+      dim3 blocks((g.NX + T - 1) / T, g.NY, g.nzl);
+      assemble_slot_kernel<NDOF><<<blocks, 9 * 32, smem, st>>>(g, ke, x, bcmask, bcdiagval, data, diag, nnz_offdiag);
+      PMB_CHECK_LAUNCH("pmb_assemble");
+      *stats_done = true;
+      return 0;
+    }
+  }
   constexpr int T = 32, NT = DIM3 ? 96 : 32;
   const size_t smem = sizeof(double) * T * NDOF * NDOF * 27;
   static bool configured = false;
@@ -190,26 +304,31 @@ static int launch_assemble(const Geo& g, const double* Ke_host, const double* x,
 }
 
 extern "C" int pmb_assemble(const pmb_grid* p, const double* Ke_host, const double* x, const unsigned char* bcmask,
-                            double bcdiagval, double* data, void* stream) {
+                            double bcdiagval, double* data, double* diag, int* nnz_offdiag, void* stream) {
   if (validate_grid(p, "pmb_assemble")) return 1;
   PMB_REQUIRE(Ke_host && x && data, "pmb_assemble: NULL pointer argument");
   Geo g = make_geo(p);
   PMB_REQUIRE(g.NY <= 65535 && g.nzl <= 65535, "pmb_assemble: grid too large for the 3-D launch");
   cudaStream_t st = (cudaStream_t)stream;
+  bool stats_done = false;
+  int rc = 1;
   if (g.dim3) {
     switch (g.ndof) {
-      case 1: return launch_assemble<1, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
-      case 2: return launch_assemble<2, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
-      case 3: return launch_assemble<3, true>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 1: rc = launch_assemble<1, true>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
+      case 2: rc = launch_assemble<2, true>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
+      case 3: rc = launch_assemble<3, true>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
     }
   } else {
     switch (g.ndof) {
-      case 1: return launch_assemble<1, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
-      case 2: return launch_assemble<2, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
-      case 3: return launch_assemble<3, false>(g, Ke_host, x, bcmask, bcdiagval, data, st);
+      case 1: rc = launch_assemble<1, false>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
+      case 2: rc = launch_assemble<2, false>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
+      case 3: rc = launch_assemble<3, false>(g, Ke_host, x, bcmask, bcdiagval, data, diag, nnz_offdiag, &stats_done, st); break;
     }
   }
-  return 1;
+  if (rc) return rc;
+  // layouts that do not produce the row statistics on the fly: one streaming pass over the values
+  if ((diag || nnz_offdiag) && !stats_done) return pmb_rowstats(p, data, diag, nnz_offdiag, stream);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------- K11

@@ -11,6 +11,7 @@
 // One thread per node: the masked x of the node's 27-neighbourhood and the densities of its 8 (4) elements are staged
 // in a shared-memory brick, the element matrix lives in the kernel-parameter constant bank so every FMA takes its
 // Ke operand straight from c[0x0][...] (compile-time indices after full unrolling).
+#include <cuda.h>
 #include <cstdlib>
 #include "pmb_tilestream.cuh"
 
@@ -214,6 +215,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NDOF, int MODE, int BY, int MINB>
 __global__ void __launch_bounds__(32 * BY, MINB)
@@ -962,91 +964,97 @@ __global__ void __launch_bounds__(256) elem_brickflags_kernel(Geo g, int nbx, in
 // ---------------------------------------------------------------------------------------------------------
 struct YmCfg {
   static constexpr int BX = 32, BZ = 2, JB = 8, NT = 256, NDOF = 3;
-  static constexpr int XLEN = (BX + 2) * NDOF, XP = 108;     // node-row pitch: 102 + shift + round-up, 12 mod 16 (bank spread)
-  static constexpr int SLEN = BX + 1, SP = 36;
-  static constexpr int XROWS = (BZ + 2) * (JB + 1), SROWS = (BZ + 1) * JB;   // 36 + 24 staging rows per step
-  static constexpr int STAGE = XROWS * XP + SROWS * SP, STAGES = 2;
+  static constexpr int XLEN = (BX + 2) * NDOF;               // doubles of a staged node row (34 nodes)
+  static constexpr int XROWS = (BZ + 2) * (JB + 1);          // node rows a step needs: 4 planes x 9 rows
+  // tensor-map TMA staging: per plane two boxes of 5 rows x 102 doubles (rows of even / odd parity, see below), each
+  // padded to 512 doubles (4096 B); one box of 34 x 8 x 3 element densities
+  static constexpr int XBOX_ROWS = 5, XREG = 512, XDOUBLES = (BZ + 2) * 2 * XREG;
+  static constexpr int SBOX_X = BX + 2, SDOUBLES = SBOX_X * JB * (BZ + 1);
+  static constexpr int STAGE = XDOUBLES + SDOUBLES, STAGES = 2;
   static constexpr int OUTW = 8 * NDOF;                      // outputs of a warp per node row
   static constexpr int SMEM_DOUBLES = STAGE * STAGES + (NT / 32) * (JB * OUTW + OUTW) + 24 * 24;
-  static_assert(STAGE % 2 == 0 && XP % 2 == 0 && SP % 2 == 0, "16-byte aligned staging rows");
-  static_assert(XROWS + SROWS <= 64, "two staging rows per lane of the producer warp");
+  static_assert(XBOX_ROWS * XLEN <= XREG && (XREG * 8) % 128 == 0 && (STAGE * 8) % 128 == 0, "TMA boxes land 128-byte aligned");
+  static_assert((XLEN * 8) % 16 == 0 && (SBOX_X * 8) % 16 == 0, "TMA box rows are whole 16-byte granules");
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(YmCfg::NT, 2)
-    elem_kernel_ym(Geo g, const __grid_constant__ KeParam<3, true> ke, int nsteps, const double* __restrict__ s,
+// TMA tensor-map loads (cp.async.bulk.tensor, SASS UTMALDG): coordinates are ELEMENT indices, innermost first; the part of
+// a box outside the tensor is zero-filled
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(YmCfg::NT, CTAS)
+    elem_kernel_ym(Geo g, const __grid_constant__ KeParam<3, true> ke, const __grid_constant__ CUtensorMap tmx,
+                   const __grid_constant__ CUtensorMap tms, int nsteps, int skew, int szoff,
                    const unsigned char* __restrict__ mask, const unsigned char* __restrict__ flags, double bcdiag,
                    const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ diag, double w,
                    double* __restrict__ y, const double* __restrict__ dotv, double* __restrict__ partials) {
   using C = YmCfg;
-  constexpr int NDOF = 3, XP = C::XP, SP = C::SP, JB = C::JB, NT = C::NT;
+  constexpr int NDOF = 3, JB = C::JB, NT = C::NT, XL = C::XLEN, XREG = C::XREG;
   extern __shared__ __align__(128) double ring[];
   double* sOut = ring + C::STAGE * C::STAGES;                 // [warp][JB][24] finished rows, then [warp][24] carry
   double* sCarry = sOut + (NT / 32) * JB * C::OUTW;
   double* sKe = sCarry + (NT / 32) * C::OUTW;
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ int done_cnt[C::STAGES];
   __shared__ double wred[3][NT / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i0 = blockIdx.x * C::BX, kl0 = blockIdx.y * C::BZ;
-  const long long Dx = (long long)(reinterpret_cast<uintptr_t>(x) >> 3), Ds = (long long)(reinterpret_cast<uintptr_t>(s) >> 3);
+  if (tid < C::STAGES) done_cnt[tid] = 0;
   const long long xrow = (long long)g.NX * NDOF;
 
-  for (int p = tid; p < C::STAGE * C::STAGES; p += NT) ring[p] = 0.0;   // stale-but-finite contract (see elem_kernel_ring)
+  for (int p = tid; p < C::STAGE * C::STAGES; p += NT) ring[p] = 0.0;   // planes that are never staged read as zeros
   for (int p = tid; p < (NT / 32) * C::OUTW; p += NT) sCarry[p] = 0.0;
   for (int p = tid; p < 24 * 24; p += NT) sKe[p] = ke.v[p];
   if (tid == 0) {
-    for (int q = 0; q < C::STAGES; ++q) mbar_init(&full_bar[q], 32);
+    for (int q = 0; q < C::STAGES; ++q) mbar_init(&full_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  // ---- producer (warp 0): staging rows of step t2 -> ring stage t2 % 2.  Node rows: plane p (kl0-1+p), row 8 t2 + rr;
-  //      density rows: layer l (kl0-1+l), element row 8 t2 + rr
+  // ---- producer (one thread): 8 + 1 tensor-map TMA loads per step instead of 60 row copies (the copy engine retires only
+  //      ~10 small bulk copies per microsecond and SM, which capped every row-staged layout at ~0.4 ms).
+  //      Node vector: a row of nodes is NX*3 doubles -- an odd number, so neither the row nor the plane stride is a multiple
+  //      of 16 bytes as a tensor map requires; TWO consecutive rows are.  The map describes the (plane-padded) vector as
+  //      [super-row = 2 node rows][2 * NX * 3 doubles]; the 9 rows of a plane that a step needs are fetched as two boxes of 5
+  //      super-rows x 102 doubles, one for the rows in the first half of their super-row and one for those in the second.
+  //      Row r of plane p lands in region (p, r & 1), slot r >> 1.  Columns that fall off a row read its neighbour row (finite,
+  //      only ever multiplied by the density of an out-of-grid element); the density box is zero-filled outside the grid by
+  //      the TMA unit itself.
   auto issue = [&](int t2) {
     const int stg = t2 % C::STAGES;
     double* su = ring + (size_t)stg * C::STAGE;
-    double* ss = su + C::XROWS * XP;
-    uintptr_t src[2];
-    double* dst[2];
-    unsigned bytes[2] = {0u, 0u};
+    unsigned bytes = C::SDOUBLES * 8u;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int r = lane + 32 * q;
-      if (r < C::XROWS) {
-        const int kl = kl0 - 1 + r / (JB + 1), j = JB * t2 + r % (JB + 1), k = g.kz0 + kl;
-        const int ia = max(i0 - 1, 0), ib = min(i0 + C::BX + 1, g.NX);
-        if (j < g.NY && k >= 0 && k < g.NZ && kl <= g.nzl && ib > ia) {
-          const long long rowb = ((long long)kl * g.NY + j) * xrow;
-          const long long D0 = Dx + rowb + (long long)(i0 - 1) * NDOF;
-          const long long lo = (Dx + rowb + (long long)ia * NDOF) & ~1LL, hi = (Dx + rowb + (long long)ib * NDOF + 1) & ~1LL;
-          src[q] = (uintptr_t)lo << 3;
-          dst[q] = su + r * XP + (int)(lo - D0 + (D0 & 1));
-          bytes[q] = (unsigned)(hi - lo) * 8u;
-        }
-      } else if (r < C::XROWS + C::SROWS) {
-        const int rs = r - C::XROWS;
-        const int el = kl0 - 1 + rs / JB, ej = JB * t2 + rs % JB, ek = g.kz0 + el;
-        const int ia = max(i0 - 1, 0), ib = min(i0 + C::BX, g.nx);
-        if (ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl && ib > ia) {
-          const long long rowb = ((long long)el * g.ny + ej) * g.nx;
-          const long long D0 = Ds + rowb + (i0 - 1);
-          const long long lo = (Ds + rowb + ia) & ~1LL, hi = (Ds + rowb + ib + 1) & ~1LL;
-          src[q] = (uintptr_t)lo << 3;
-          dst[q] = ss + rs * SP + (int)(lo - D0 + (D0 & 1));
-          bytes[q] = (unsigned)(hi - lo) * 8u;
-        }
+    for (int p = 0; p < C::BZ + 2; ++p) {
+      const int klp = kl0 - 1 + p, k = g.kz0 + klp;
+      if (k >= 0 && k < g.NZ && klp <= g.nzl) bytes += 2u * C::XBOX_ROWS * XL * 8u;
+    }
+    mbar_expect_tx(&full_bar[stg], bytes);
+#pragma unroll
+    for (int p = 0; p < C::BZ + 2; ++p) {
+      const int klp = kl0 - 1 + p, k = g.kz0 + klp;
+      if (k >= 0 && k < g.NZ && klp <= g.nzl) {   // planes outside the grid / beyond the upper halo stay zero
+        const int R0 = (klp + 1) * g.NY + JB * t2, a = R0 & 1;   // row index in the map (its first plane is local plane -1)
+        tma_load_2d(su + (2 * p) * XREG, &tmx, a * (int)xrow + (i0 - 1) * NDOF, R0 >> 1, &full_bar[stg]);
+        tma_load_2d(su + (2 * p + 1) * XREG, &tmx, (1 - a) * (int)xrow + (i0 - 1) * NDOF, (R0 + 1) >> 1, &full_bar[stg]);
       }
     }
-    const unsigned total = bytes[0] + bytes[1];
-    if (total) mbar_expect_tx(&full_bar[stg], total);
-    else mbar_arrive(&full_bar[stg]);
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (bytes[q]) tma_load_1d(dst[q], reinterpret_cast<const void*>(src[q]), bytes[q], &full_bar[stg], false);
+    tma_load_3d(su + C::XDOUBLES, &tms, i0 - 1, JB * t2, kl0 - 1 + szoff, &full_bar[stg]);
   };
-  if (warp == 0)
+  if (tid == 0)
     for (int t2 = 0; t2 < C::STAGES && t2 < nsteps; ++t2) issue(t2);
 
   // ---- consumer role of this warp: node columns i = iw .. iw+7 of plane kl
@@ -1068,8 +1076,6 @@ __global__ void __launch_bounds__(YmCfg::NT, 2)
       }
   // B fragment offsets (doubles inside a ring stage, element column offset excluded): k index kk = 4 ks + q4 = 3 bn + c,
   // column gq = element row; node (bx, gq + by, bz) of the element, layer selector az (element layer = kl - az)
-  const int P0 = (int)((Dx + ((long long)(kl0 - 1) * g.NY) * xrow + (long long)(i0 - 1) * NDOF) & 1);
-  const int pkx = (int)(((long long)g.NY * xrow) & 1), pjx = (int)(xrow & 1);
   int boff[2][6];
 #pragma unroll
   for (int az = 0; az < 2; ++az)
@@ -1078,22 +1084,19 @@ __global__ void __launch_bounds__(YmCfg::NT, 2)
       const int kk = 4 * ks + q4, bn = kk / 3, c = kk - 3 * bn;
       const int bx = bn & 1, by = (bn >> 1) & 1, bz = bn >> 2;
       const int p = wz + 1 - az + bz, row = gq + by;
-      boff[az][ks] = (p * (JB + 1) + row) * XP + bx * NDOF + c + ((P0 + p * pkx + row * pjx) & 1);
+      boff[az][ks] = (2 * p + (row & 1)) * XREG + (row >> 1) * XL + bx * NDOF + c;
     }
-  const int Ps0 = (int)((Ds + ((long long)(kl0 - 1) * g.ny) * g.nx + (i0 - 1)) & 1);
-  const int pks = (int)(((long long)g.ny * g.nx) & 1), pjs = g.nx & 1;
   int soff[2][2];
 #pragma unroll
   for (int az = 0; az < 2; ++az)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int l = wz + 1 - az, row = 2 * q4 + h;
-      soff[az][h] = C::XROWS * XP + (l * JB + row) * SP + ((Ps0 + l * pks + row * pjs) & 1);
-    }
+    for (int h = 0; h < 2; ++h) soff[az][h] = C::XDOUBLES + ((wz + 1 - az) * JB + 2 * q4 + h) * C::SBOX_X;
   double* myOut = sOut + warp * JB * C::OUTW;
   double* myCarry = sCarry + warp * C::OUTW;
   const int nbxg = gridDim.x;
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+  const int dbg = skew;  // diagnostic bit mask (PMB_YM_SKEW): 1 = no epilogue, 2 = no DMMA, 4 = no B / s shared loads, 8 = no finalize
+  bool fnext = flags ? __ldg(flags + ((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps) != 0 : true;
 
   for (int t = 0; t <= nsteps; ++t) {
     const bool flush = t == nsteps;       // last pass: only the carried row (node row 8 nsteps, when it exists)
@@ -1103,28 +1106,23 @@ __global__ void __launch_bounds__(YmCfg::NT, 2)
     const int j0 = JB * t;
     bool flagged = false;
     if (!flush) {
-      flagged = mask && (flags ? flags[((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps + t] != 0 : true);
-      const bool edge = i0 == 0 || i0 + C::BX > g.nx || j0 + JB > g.ny || g.kz0 + kl0 == 0 || g.kz0 + kl0 + C::BZ > g.nzE ||
-                        kl0 + C::BZ > g.nzl;
+      flagged = mask && fnext;
+      // next step's flag and this step's epilogue operands start their trip through the memory system now
+      if (flags && t + 1 < nsteps) fnext = __ldg(flags + ((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps + t + 1) != 0;
+      if (wactive && lane < 16 && j0 + (lane >> 1) < g.NY) {
+        const long long pr = (((long long)kl * g.NY + j0 + (lane >> 1)) * g.NX + iw) * NDOF + 16 * (lane & 1);
+        if (MODE != EMODE_SPMV) prefetch_l2(b + pr);
+        if (MODE == EMODE_JACOBI) prefetch_l2(diag + pr), prefetch_l2(x + pr);
+      }
       mbar_wait(&full_bar[stg], (unsigned)((t / C::STAGES) & 1));
-      if (edge || flagged) {
-        double* ss = su + C::XROWS * XP;
-        if (edge) {
-          for (int p = tid; p < C::SROWS * C::SLEN; p += NT) {
-            const int rs = p / C::SLEN, c = p - rs * C::SLEN;
-            const int el = kl0 - 1 + rs / JB, ej = j0 + rs % JB, ek = g.kz0 + el, ei = i0 - 1 + c;
-            const bool ok = ei >= 0 && ei < g.nx && ej < g.ny && ek >= 0 && ek < g.nzE && el < g.nzl;
-            if (!ok) ss[rs * SP + c + (int)((Ds + ((long long)el * g.ny + ej) * g.nx + (i0 - 1)) & 1)] = 0.0;
-          }
-        }
-        if (flagged) {
-          for (int p = tid; p < C::XROWS * C::XLEN; p += NT) {
-            const int r = p / C::XLEN, c = p - r * C::XLEN;
-            const int klr = kl0 - 1 + r / (JB + 1), jr = j0 + r % (JB + 1), kr = g.kz0 + klr, ir = i0 - 1 + c / NDOF;
-            if (ir >= 0 && ir < g.NX && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl) {
-              const long long rowb = ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF;
-              if (__ldg(mask + rowb + c)) su[r * XP + c + (int)((Dx + rowb) & 1)] = 0.0;
-            }
+      if (flagged) {   // Dirichlet columns of the staged rows are zeroed in place (CTA-uniform, rare)
+        for (int p = tid; p < C::XROWS * XL; p += NT) {
+          const int rr = p / XL, c = p - rr * XL;
+          const int pl = rr / (JB + 1), r = rr - pl * (JB + 1);
+          const int klr = kl0 - 1 + pl, jr = j0 + r, kr = g.kz0 + klr, ir = i0 - 1 + c / NDOF;
+          if (ir >= 0 && ir < g.NX && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl) {
+            const long long rowb = ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF;
+            if (__ldg(mask + rowb + c)) su[(2 * pl + (r & 1)) * XREG + (r >> 1) * XL + c] = 0.0;
           }
         }
         __syncthreads();
@@ -1141,28 +1139,47 @@ __global__ void __launch_bounds__(YmCfg::NT, 2)
           double ycur[2] = {ynext[0], ynext[1]};
           ynext[0] = ynext[1] = 0.0;
           const int coloff = (8 * wx + ex + 1) * NDOF;
+          // both element layers of the column at once, every 24-long dot product split into two 12-long halves: up to 8
+          // independent DMMA chains of depth 3 per warp (a dependent DMMA issues only every ~100 cycles, and the FP64 tensor
+          // pipe needs ~8 independent accumulations per scheduler to stay busy)
+          double bv[2][6], sv[2][2];
 #pragma unroll
           for (int az = 0; az < 2; ++az) {
-            double bv[6];
 #pragma unroll
-            for (int ks = 0; ks < 6; ++ks) bv[ks] = su[boff[az][ks] + coloff];
-            const double s0 = su[soff[az][0] + 8 * wx + ex + 1], s1 = su[soff[az][1] + 8 * wx + ex + 1];
+            for (int ks = 0; ks < 6; ++ks) bv[az][ks] = (dbg & 4) ? 1.0 + ks + lane : su[boff[az][ks] + coloff];
+            sv[az][0] = (dbg & 4) ? 1.0 : su[soff[az][0] + 8 * wx + ex + 1];
+            sv[az][1] = (dbg & 4) ? 1.0 : su[soff[az][1] + 8 * wx + ex + 1];
+          }
+          double cc[2][2][2][2];  // [az][ax][half][c0 / c1]
+#pragma unroll
+          for (int az = 0; az < 2; ++az)
+#pragma unroll
+            for (int ax = 0; ax < 2; ++ax)
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) cc[az][ax][hf][0] = cc[az][ax][hf][1] = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+            for (int az = 0; az < 2; ++az)
+#pragma unroll
+              for (int ax = 0; ax < 2; ++ax) {
+                if ((ax == 0 && ex < 0) || (ax == 1 && ex > 6)) continue;  // node column outside this warp's eight
+                if (dbg & 2) continue;
+                dmma884(cc[az][ax][0][0], cc[az][ax][0][1], af[az][ax][ks], bv[az][ks]);
+                dmma884(cc[az][ax][1][0], cc[az][ax][1][1], af[az][ax][ks + 3], bv[az][ks + 3]);
+              }
+#pragma unroll
+          for (int az = 0; az < 2; ++az) {
             if (ex >= 0) {   // ax = 0: this element column's own node column
-              double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-              for (int ks = 0; ks < 6; ++ks) dmma884(c0, c1, af[az][0][ks], bv[ks]);
-              ycur[0] = fma(s0, c0, ycur[0]);
-              ycur[1] = fma(s1, c1, ycur[1]);
+              ycur[0] = fma(sv[az][0], cc[az][0][0][0] + cc[az][0][1][0], ycur[0]);
+              ycur[1] = fma(sv[az][1], cc[az][0][0][1] + cc[az][0][1][1], ycur[1]);
             }
             if (ex < 7) {    // ax = 1: the node column to the right
-              double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-              for (int ks = 0; ks < 6; ++ks) dmma884(c0, c1, af[az][1][ks], bv[ks]);
-              ynext[0] = fma(s0, c0, ynext[0]);
-              ynext[1] = fma(s1, c1, ynext[1]);
+              ynext[0] = fma(sv[az][0], cc[az][1][0][0] + cc[az][1][1][0], ynext[0]);
+              ynext[1] = fma(sv[az][1], cc[az][1][0][1] + cc[az][1][1][1], ynext[1]);
             }
           }
-          if (ex >= 0) {
+          if (ex >= 0 && !(dbg & 8)) {
             // ---- node column di = ex finished: lane (row gq = (ay, d), cols 2 q4, 2 q4 + 1).  Node row c takes (ay = 0,
             //      col c) + (ay = 1, col c - 1); col -1 is the value carried from the previous step
             const int srcrow = (gq % 3 + 3) * 4;                              // lane base of row (ay = 1, d)
@@ -1183,13 +1200,23 @@ __global__ void __launch_bounds__(YmCfg::NT, 2)
       __syncwarp();
     }
     if (!flush) {
-      __syncthreads();  // every warp is done with ring stage stg (the epilogue below reads global memory only)
-      if (warp == 0 && t + C::STAGES < nsteps) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(t + C::STAGES);
+      // ---- release ring stage stg without a CTA barrier: the LAST warp to leave it refills it for step t + 2 (the epilogue
+      //      below reads global memory only), so fast warps run on into their epilogue / next step instead of waiting
+      __threadfence_block();  // this warp's reads of the stage are complete before it signs off
+      int prev = 0;
+      if (lane == 0) prev = atomicAdd(&done_cnt[stg], 1);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == NT / 32 - 1) {
+        if (lane == 0) {
+          done_cnt[stg] = 0;  // next touched after the refill below has landed and been consumed
+          if (t + C::STAGES < nsteps) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + C::STAGES);
+          }
+        }
       }
     }
-    if (wactive) {
+    if (wactive && !(dbg & 1)) {
       // ---- epilogue: 8 node rows x 24 contiguous doubles (8 nodes x 3 dofs) of this warp; lane < 24 owns one column of
       //      them.  All loads of 4 rows are issued before the first use.
       const int nrows = flush ? 1 : JB;
@@ -1287,7 +1314,7 @@ static void ym_grid(const Geo& g, int& nbx, int& nbz, int& nsteps) {
 extern "C" long long pmb_elem_brickflags_bytes(const pmb_grid* p, int variant) {
   if (validate_grid(p, "pmb_elem_brickflags_bytes")) return -1;
   Geo g = make_geo(p);
-  if (variant == 6) {
+  if (variant == 6 || variant == 7) {
     int nbx, nbz, nsteps;
     ym_grid(g, nbx, nbz, nsteps);
     return (long long)nbx * nbz * nsteps;
@@ -1301,10 +1328,10 @@ extern "C" int pmb_elem_brickflags(const pmb_grid* p, int variant, const unsigne
   if (validate_grid(p, "pmb_elem_brickflags")) return 1;
   PMB_REQUIRE(bcmask && flags, "pmb_elem_brickflags: NULL pointer argument");
   PMB_REQUIRE(p->nz > 0, "pmb_elem_brickflags: 3-D grids only");
-  PMB_REQUIRE(variant == 4 || variant == 5 || variant == 6, "pmb_elem_brickflags: layout %d takes no flags", variant);
+  PMB_REQUIRE(variant >= 4 && variant <= 7, "pmb_elem_brickflags: layout %d takes no flags", variant);
   Geo g = make_geo(p);
-  if (variant == 6) {
-    PMB_REQUIRE(g.ndof == 3, "pmb_elem_brickflags: layout 6 is ndof = 3 only");
+  if (variant == 6 || variant == 7) {
+    PMB_REQUIRE(g.ndof == 3, "pmb_elem_brickflags: layouts 6, 7 are ndof = 3 only");
     int nbx, nbz, nsteps;
     ym_grid(g, nbx, nbz, nsteps);
     PMB_REQUIRE(nbx <= 65535 && nbz <= 65535, "pmb_elem_brickflags: grid too large");
@@ -1349,12 +1376,12 @@ static dim3 elem_grid(const Geo& g) {
 //      staged bricks (elem_kernel_ring) at 3 / 2 CTAs per SM, 6 = y-marching FP64 tensor-core layout with in-register
 //      accumulation (elem_kernel_ym, ndof 3 only).  The layout is a field of the caller's pmb_elem_op: no process-wide state.
 //      Layouts 0, 1, 2, 4, 5 produce bit-identical y; 3 and 6 (tensor-core accumulation order) agree to rounding.
-enum { PMB_ELEM_VARIANTS = 7 };
+enum { PMB_ELEM_VARIANTS = 8 };
 extern "C" int pmb_elem_num_variants(void) { return PMB_ELEM_VARIANTS; }
 
 static int effective_variant(const Geo& g, int variant) {
   if (!g.dim3 || g.ndof == 2) return 0;
-  if ((variant == 3 || variant == 6) && g.ndof != 3) return 0;
+  if ((variant == 3 || variant == 6 || variant == 7) && g.ndof != 3) return 0;
   return variant;
 }
 
@@ -1375,7 +1402,8 @@ static dim3 elem_grid_any(const Geo& g, int variant) {
       const long long nb = (long long)nbx * nby * nbz, cap = (variant == 4 ? 3LL : 2LL) * sm_count_elem();
       return dim3((unsigned)(nb < cap ? nb : cap), 1, 1);
     }
-    case 6: {
+    case 6:
+    case 7: {
       int nbx, nbz, nsteps;
       ym_grid(g, nbx, nbz, nsteps);
       return dim3(nbx, nbz, 1);
@@ -1396,6 +1424,60 @@ extern "C" long long pmb_elem_ws_doubles(const pmb_grid* p) {
   return m;
 }
 
+// ---- tensor maps of the y-marching layout (see elem_kernel_ym): the node vector as [2-row super-rows][2 * NX * 3] starting at
+//      the plane below the slab (x must live in plane-padded storage whose first pad plane is 16-byte aligned:
+//      DeviceCSR.new_vec()), the element scaling vector as a plain [layers][ny][nx] tensor of its valid layers
+typedef CUresult (*pmb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pmb_encode_tiled_fn encode_tiled_entry() {
+  static pmb_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (pmb_encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+static bool ym_layout_applicable(const Geo& g, const double* x, const double* s) {
+  const long long plane = (long long)g.NX * g.NY * 3;
+  return g.dim3 && g.ndof == 3 && (g.nx % 2) == 0 && ((reinterpret_cast<uintptr_t>(x) - 8ull * plane) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(s) & 15) == 0 && encode_tiled_entry() != nullptr;
+}
+
+static int ym_tensor_maps(const Geo& g, const double* x, const double* s, CUtensorMap* tmx, CUtensorMap* tms, int* szoff) {
+  pmb_encode_tiled_fn enc = encode_tiled_entry();
+  PMB_REQUIRE(enc, "pmb_elem_spmv: cuTensorMapEncodeTiled not available in this driver");
+  const cuuint64_t xrow = (cuuint64_t)g.NX * 3, plane = xrow * g.NY;
+  const cuuint64_t rows = (cuuint64_t)(g.nzl + 2) * g.NY;
+  {
+    cuuint64_t dims[2] = {2 * xrow, (rows + 1) / 2};
+    cuuint64_t strides[1] = {2 * xrow * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)YmCfg::XLEN, (cuuint32_t)YmCfg::XBOX_ROWS};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x) - plane, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pmb_set_error("pmb_elem_spmv: tensor map of the node vector rejected (CUresult %d)", (int)r);
+  }
+  {
+    const int below = g.kz0 > 0 ? 1 : 0;   // the halo layer under the slab exists only inside the grid
+    const int nlay = (g.nzl < g.nzE - g.kz0 ? g.nzl : g.nzE - g.kz0) + below;
+    cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)(nlay > 0 ? nlay : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)g.nx * sizeof(double), (cuuint64_t)g.nx * g.ny * sizeof(double)};
+    cuuint32_t box[3] = {(cuuint32_t)YmCfg::SBOX_X, (cuuint32_t)YmCfg::JB, (cuuint32_t)(YmCfg::BZ + 1)};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(tms, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(s) - (size_t)below * g.nx * g.ny, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return pmb_set_error("pmb_elem_spmv: tensor map of the element scaling vector rejected (CUresult %d)", (int)r);
+    *szoff = below;
+  }
+  return 0;
+}
+
 template <int NDOF, bool DIM3, int MODE>
 static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, const double* b, const double* diag, double w,
                        double* y, const double* dotv, double* dot_out, double* ws, cudaStream_t st) {
@@ -1404,7 +1486,8 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
   const double* s = op->s;
   const unsigned char* mask = op->bcmask;
   const double bcdiag = op->bcdiagval;
-  const int variant = effective_variant(g, op->variant);
+  int variant = effective_variant(g, op->variant);
+  if ((variant == 6 || variant == 7) && !ym_layout_applicable(g, x, s)) variant = 0;  // odd nx / unpadded or misaligned storage
   dim3 grid = elem_grid_any(g, variant);
   double* part = dot_out ? ws : nullptr;
   if constexpr (DIM3 && NDOF != 2) {
@@ -1423,19 +1506,29 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
         }
         elem_kernel_mma<MODE><<<grid, MM_NT, smem, st>>>(g, ke, mma_zl(g), s, mask, bcdiag, x, b, diag, w, y, dotv, part);
       }
-    } else if (variant == 6) {
+    } else if (variant == 6 || variant == 7) {
       if constexpr (NDOF == 3) {
         constexpr size_t smem = sizeof(double) * YmCfg::SMEM_DOUBLES;
         static bool configured = false;
         if (!configured) {
-          cudaError_t e = cudaFuncSetAttribute(elem_kernel_ym<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          cudaError_t e = cudaFuncSetAttribute(elem_kernel_ym<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(elem_kernel_ym<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return pmb_set_error("elem_kernel_ym attribute: %s", cudaGetErrorString(e));
           configured = true;
         }
         int nbx, nbz, nsteps;
         ym_grid(g, nbx, nbz, nsteps);
         PMB_REQUIRE(nbz <= 65535, "pmb_elem_spmv: slab too tall for the y-marching layout");
-        elem_kernel_ym<MODE><<<grid, YmCfg::NT, smem, st>>>(g, ke, nsteps, s, mask, op->brickflags, bcdiag, x, b, diag, w, y, dotv, part);
+        static const int ym_skew = getenv("PMB_YM_SKEW") ? atoi(getenv("PMB_YM_SKEW")) : 0;
+        CUtensorMap tmx, tms;
+        int szoff = 0;
+        if (ym_tensor_maps(g, x, s, &tmx, &tms, &szoff)) return 1;
+        if (variant == 6)
+          elem_kernel_ym<MODE, 2><<<grid, YmCfg::NT, smem, st>>>(g, ke, tmx, tms, nsteps, ym_skew, szoff, mask, op->brickflags, bcdiag, x, b,
+                                                                 diag, w, y, dotv, part);
+        else
+          elem_kernel_ym<MODE, 1><<<grid, YmCfg::NT, smem, st>>>(g, ke, tmx, tms, nsteps, ym_skew, szoff, mask, op->brickflags, bcdiag, x, b,
+                                                                 diag, w, y, dotv, part);
       }
     } else if (variant == 4 || variant == 5) {
       using C = RingCfg<NDOF>;
@@ -1536,9 +1629,9 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const
   for (int v = 0; v < PMB_ELEM_VARIANTS && !rc; ++v) {
     trial.variant = v;
     trial.brickflags = nullptr;
-    const bool wants_flags = (v == 4 || v == 5 || (v == 6 && p->ndof == 3)) && p->ndof != 2;
+    const bool wants_flags = (v == 4 || v == 5 || ((v == 6 || v == 7) && p->ndof == 3)) && p->ndof != 2;
     if (op->bcmask && wants_flags) {
-      if (v != 5) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 reuses the flags of 4
+      if (v != 5 && v != 7) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 / 7 reuse the flags of 4 / 6
       trial.brickflags = flags_scratch;
     }
     const int reps = 6;
@@ -1552,7 +1645,7 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= reps;
     if (ms_out) ms_out[v] = ms;
-    const bool rounding = (v == 3 || v == 6) && p->ndof == 3;
+    const bool rounding = (v == 3 || v == 6 || v == 7) && p->ndof == 3;
     if (!rc && ms < best_ms && (allow_rounding || !rounding)) best_ms = ms, best = v;
   }
   cudaEventDestroy(e0);

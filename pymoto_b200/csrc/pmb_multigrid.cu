@@ -362,21 +362,22 @@ extern "C" int pmb_galerkin_rows(const pmb_grid* pf, const pmb_grid* pc, const d
 // ------------------------------------------------------------------------------------------------- K6 (direct)
 // Level-1 operator straight from the element densities (host set-up and derivation: pymoto_b200/coarse.py):
 //     Ac = sum_E sum_{p<8} s_child(E,p) G_id(E,p)  [+ the Dirichlet diagonal term, added by pmb_scatter_add]
-// One warp = 32 consecutive coarse nodes of an x-row x ONE neighbour slot (27 warps per CTA): the element / local-node
-// structure is warp-uniform, so the table entry G[id][a][b] is a shared-memory broadcast for unmasked children (id = p)
+// One warp = 32 consecutive coarse nodes of an x-row x ONE (dk, dj) line of neighbour slots (9 warps per CTA, the three di
+// slots in turn; 2 CTAs per SM so that one CTA computes while another writes out): the element / local-node structure is
+// warp-uniform, so the table entry G[id][a][b] is a shared-memory broadcast for unmasked children (id = p)
 // and only coarse elements with a Dirichlet child (cidx >= 0) read per-child ids and the table in global memory.
 // The CTA builds the contiguous run of its 32 nodes in shared memory (same layout as assemble_kernel) and writes it
 // with coalesced stores.  Densities of the 66 x 4 x 4 fine elements around the run are staged once (0.0 outside the grid).
 template <int NDOF>
-__global__ void __launch_bounds__(27 * 32, 1)
+__global__ void __launch_bounds__(9 * 32, 2)
     galerkin_direct_kernel(Geo gf, Geo gc, const double* __restrict__ Gtab, const int* __restrict__ cidx,
                            const unsigned short* __restrict__ child_ids, const double* __restrict__ s, double* __restrict__ Ac) {
-  constexpr int T = 32, ND2 = NDOF * NDOF, NT = 27 * 32, SW = 2 * T + 2;
+  constexpr int T = 32, ND2 = NDOF * NDOF, NT = 9 * 32, SW = 2 * T + 2;
   extern __shared__ double dyn[];
   double* tile = dyn;                    // T * ND2 * 27 doubles: the output run
   double* sG = tile + T * ND2 * 27;      // 8 * 64 * ND2: unmasked child tables
   double* sS = sG + 8 * 64 * ND2;        // 4 x 4 x SW staged densities
-  const int tid = threadIdx.x, gI = tid & 31, slot = tid >> 5;
+  const int tid = threadIdx.x, gI = tid & 31, line = tid >> 5;
   const int I0 = blockIdx.x * T, J = blockIdx.y, kl = blockIdx.z, K = gc.kz0 + kl;
   const int ni = min(T, gc.NX - I0);
   for (int p = tid; p < 8 * 64 * ND2; p += NT) sG[p] = Gtab[p];
@@ -397,54 +398,60 @@ __global__ void __launch_bounds__(27 * 32, 1)
   const long long e0 = (long long)ND2 * rowbase + per * pre1(I0, gc.NX);
   const int nelem = (int)(per * (pre1(I0 + ni, gc.NX) - pre1(I0, gc.NX)));
 
-  const int dk = slot / 9 - 1, dj = (slot / 3) % 3 - 1, di = slot % 3 - 1;   // warp-uniform
-  const int I = I0 + gI, CI = I + di, CJ = J + dj, CK = K + dk;
-  if (gI < ni && CI >= 0 && CI < gc.NX && CJ >= 0 && CJ < gc.NY && CK >= 0 && CK < gc.NZ) {
-    double acc[ND2];
+  const int dk = line / 3 - 1, dj = line % 3 - 1;   // warp-uniform: one (dk, dj) line of neighbour slots per warp
+  const int I = I0 + gI, CJ = J + dj, CK = K + dk;
+  if (gI < ni && CJ >= 0 && CJ < gc.NY && CK >= 0 && CK < gc.NZ) {
+    const int cx = cnt1(I, gc.NX), Ilo = max(I - 1, 0);
+    const int L = cx * cy * cz * NDOF;
 #pragma unroll
-    for (int q = 0; q < ND2; ++q) acc[q] = 0.0;
-    for (int oz = 0; oz < 2; ++oz) {
-      const int az = 1 - oz, bz = az + dk, EK = K - 1 + oz;
-      if (bz < 0 || bz > 1 || EK < 0 || EK >= gc.nzE) continue;
-      for (int oy = 0; oy < 2; ++oy) {
-        const int ay = 1 - oy, by = ay + dj, EJ = J - 1 + oy;
-        if (by < 0 || by > 1 || EJ < 0 || EJ >= gc.ny) continue;
-        for (int ox = 0; ox < 2; ++ox) {
-          const int ax = 1 - ox, bx = ax + di, EI = I - 1 + ox;
-          if (bx < 0 || bx > 1) continue;        // warp-uniform
-          if (EI < 0 || EI >= gc.nx) continue;   // per lane (first / last node of the row)
-          const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
-          const int m = cidx ? __ldg(cidx + ((long long)EK * gc.ny + EJ) * gc.nx + EI) : -1;
-          const double* sp = sS + ((2 * oz) * 4 + 2 * oy) * SW + 2 * (gI + ox);
-          if (m < 0) {
-            const double* gp = sG + (a * 8 + bn) * ND2;
+    for (int di = -1; di <= 1; ++di) {
+      const int CI = I + di;
+      if (CI < 0 || CI >= gc.NX) continue;
+      double acc[ND2];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
+      for (int q = 0; q < ND2; ++q) acc[q] = 0.0;
+      for (int oz = 0; oz < 2; ++oz) {
+        const int az = 1 - oz, bz = az + dk, EK = K - 1 + oz;
+        if (bz < 0 || bz > 1 || EK < 0 || EK >= gc.nzE) continue;
+        for (int oy = 0; oy < 2; ++oy) {
+          const int ay = 1 - oy, by = ay + dj, EJ = J - 1 + oy;
+          if (by < 0 || by > 1 || EJ < 0 || EJ >= gc.ny) continue;
 #pragma unroll
-              for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, gp[p * 64 * ND2 + q], acc[q]);
-            }
-          } else {
-            const unsigned short* ids = child_ids + 8 * (long long)m;
+          for (int ox = 0; ox < 2; ++ox) {
+            const int ax = 1 - ox, bx = ax + di, EI = I - 1 + ox;
+            if (bx < 0 || bx > 1) continue;        // compile-time
+            if (EI < 0 || EI >= gc.nx) continue;   // per lane (first / last node of the row)
+            const int a = ax + 2 * ay + 4 * az, bn = bx + 2 * by + 4 * bz;
+            const int m = cidx ? __ldg(cidx + ((long long)EK * gc.ny + EJ) * gc.nx + EI) : -1;
+            const double* sp = sS + ((2 * oz) * 4 + 2 * oy) * SW + 2 * (gI + ox);
+            if (m < 0) {
+              const double* gp = sG + (a * 8 + bn) * ND2;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-              const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
-              const double* gp = Gtab + ((long long)__ldg(ids + p) * 64 + a * 8 + bn) * ND2;
+              for (int p = 0; p < 8; ++p) {
+                const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
 #pragma unroll
-              for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, __ldg(gp + q), acc[q]);
+                for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, gp[p * 64 * ND2 + q], acc[q]);
+              }
+            } else {
+              const unsigned short* ids = child_ids + 8 * (long long)m;
+#pragma unroll
+              for (int p = 0; p < 8; ++p) {
+                const double sv = sp[((p >> 2) * 4 + ((p >> 1) & 1)) * SW + (p & 1)];
+                const double* gp = Gtab + ((long long)__ldg(ids + p) * 64 + a * 8 + bn) * ND2;
+#pragma unroll
+                for (int q = 0; q < ND2; ++q) acc[q] = fma(sv, __ldg(gp + q), acc[q]);
+              }
             }
           }
         }
       }
+      const int nbr = ((CK - Klo) * cy + (CJ - Jlo)) * cx + (CI - Ilo);
+      double* nodep = tile + per * (pre1(I, gc.NX) - pre1(I0, gc.NX)) + nbr * NDOF;
+#pragma unroll
+      for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) nodep[d * L + c] = acc[d * NDOF + c];
     }
-    const int cx = cnt1(I, gc.NX), Ilo = max(I - 1, 0);
-    const int L = cx * cy * cz * NDOF;
-    const int nbr = ((CK - Klo) * cy + (CJ - Jlo)) * cx + (CI - Ilo);
-    double* nodep = tile + per * (pre1(I, gc.NX) - pre1(I0, gc.NX)) + nbr * NDOF;
-#pragma unroll
-    for (int d = 0; d < NDOF; ++d)
-#pragma unroll
-      for (int c = 0; c < NDOF; ++c) nodep[d * L + c] = acc[d * NDOF + c];
   }
   __syncthreads();
   for (int q = tid; q < nelem; q += NT) Ac[e0 + q] = tile[q];
@@ -462,7 +469,7 @@ static int launch_galerkin_direct(const Geo& gf, const Geo& gc, const double* Gt
     configured = true;
   }
   dim3 blocks((gc.NX + T - 1) / T, gc.NY, gc.nzl);
-  galerkin_direct_kernel<NDOF><<<blocks, 27 * 32, smem, st>>>(gf, gc, Gtab, cidx, child_ids, s, Ac);
+  galerkin_direct_kernel<NDOF><<<blocks, 9 * 32, smem, st>>>(gf, gc, Gtab, cidx, child_ids, s, Ac);
   PMB_CHECK_LAUNCH("pmb_galerkin_direct");
   return 0;
 }

@@ -130,6 +130,7 @@ extern "C" int pmb_pcg_solve(const pmb_mg_desc* mg, const double* b, double* x, 
     *iters = i + 1;
     *relres = tval;
     if (tval <= tol) break;
+    if (!std::isfinite(tval)) return pmb_set_error("pmb_pcg_solve: residual became non-finite in iteration %d (singular operator or preconditioner)", i);
     if (vcycle(mg, 0, r, &z, stream)) return 1;
     if (pmb_dots(n, 1, q, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, qz, ws_red, stream)) return 1;
     const pmb_coef beta = {-1.0, qz, pq, 0};

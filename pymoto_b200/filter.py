@@ -48,6 +48,9 @@ class DensityFilter(Module):
         self.Hs = dv.empty(self.nel)
         self._apply(None, None, self.Hs)
         if nonpadding is not None:  # filter.py:253-255
+            if ctx.active:
+                raise NotImplementedError("pymoto_b200.DensityFilter(nonpadding=...) is not distributed over z-slabs "
+                                          "(global element numbers and a global max of Hs are involved)")
             keep = torch.zeros(self.nel, dtype=torch.bool, device=self.Hs.device)
             keep[dv.to_device(np.asarray(nonpadding).ravel(), torch.int64)] = True
             self.Hs = torch.where(keep, self.Hs, self.Hs.max())
@@ -96,8 +99,6 @@ class FilterConv(Module):
     def __init__(self, domain, radius: float = None, relative_units: bool = True, weights=None, xmin_bc="symmetric",
                  xmax_bc="symmetric", ymin_bc="symmetric", ymax_bc="symmetric", zmin_bc="symmetric", zmax_bc="symmetric"):
         dv.require_cuda()
-        if slab.context().active:
-            raise NotImplementedError("FilterConv is single-GPU in this build; use DensityFilter for slab-decomposed runs")
         self.domain = domain
         self.weights = None
         if (weights is None and radius is None) or (weights is not None and radius is not None):
@@ -111,21 +112,44 @@ class FilterConv(Module):
         else:
             self.set_filter_radius(radius, relative_units)
         nx, ny, nz = grid_dims(domain)
-        self._n = (nx, ny, max(nz, 1))
-        self.nel = nx * ny * max(nz, 1)
         self.pad_sizes = [v // 2 for v in self.weights.shape]
-        self._p = tuple(n + 2 * p for n, p in zip(self._n, self.pad_sizes))
+        maps = [self._axis_map(n, self.pad_sizes[a], bc0, bc1)
+                for a, (n, (bc0, bc1)) in enumerate(zip((nx, ny, max(nz, 1)), [(xmin_bc, xmax_bc), (ymin_bc, ymax_bc), (zmin_bc, zmax_bc)]))]
+        # slab decomposition: this rank filters its element layers [e0, e1).  The "source" field of the kernels is then the
+        # rank's layers plus pz halo layers on each side (filled from the z-neighbours), and the z map is the window
+        # [e0, e1 + 2 pz) of the global one re-based to that extended field; global faces keep their boundary treatment.
+        self._ctx = ctx = slab.context(nz)
+        self._halo = 0
+        if ctx.active:
+            pz = self.pad_sizes[2]
+            e0, e1 = ctx.part.elem_layers(0)
+            if "wrap" in (zmin_bc, zmax_bc):
+                raise NotImplementedError("FilterConv: z wrap-around boundaries are not available under a slab decomposition")
+            if e1 - e0 < pz:
+                raise ValueError(f"FilterConv kernel needs at least {pz} element layers per rank (have {e1 - e0})")
+            mz, cz = maps[2]
+            win = mz[e0: e1 + 2 * pz].copy()
+            loc = np.where(win >= 0, win - (e0 - pz), -1)
+            assert np.all((loc < e1 - e0 + 2 * pz)), "boundary treatment reaches beyond the neighbouring slab"
+            maps[2] = (loc, cz[e0: e1 + 2 * pz].copy())
+            self._halo, self._lay, self._nown = pz, nx * ny, (e1 - e0)
+            self._n = (nx, ny, e1 - e0 + 2 * pz)          # source extent seen by the gather / scatter kernels
+            self._nout = (nx, ny, e1 - e0)                # layers this rank produces
+            self._p = (nx + 2 * self.pad_sizes[0], ny + 2 * self.pad_sizes[1], e1 - e0 + 2 * pz)
+            self.nel = nx * ny * (e1 - e0)
+        else:
+            self._n = self._nout = (nx, ny, max(nz, 1))
+            self.nel = nx * ny * max(nz, 1)
+            self._p = tuple(n + 2 * p for n, p in zip(self._n, self.pad_sizes))
         self.overrides = []  # user overrides: (flat padded indices (device int64), value)
-        maps = [self._axis_map(self._n[a], self.pad_sizes[a], bc0, bc1)
-                for a, (bc0, bc1) in enumerate([(xmin_bc, xmax_bc), (ymin_bc, ymax_bc), (zmin_bc, zmax_bc)])]
         self._map = [dv.to_device(m[0].astype(np.int32), torch.int32) for m in maps]
         self._cval = [dv.to_device(m[1]) for m in maps]
         # inverse maps (which padded positions read a given source index), CSR form, for the backward scatter
         self._inv = []
-        for m, _ in maps:
+        for a, (m, _) in enumerate(maps):
             order = np.argsort(m, kind="stable")
             order = order[m[order] >= 0]
-            counts = np.bincount(m[m >= 0], minlength=0)
+            counts = np.bincount(m[m >= 0], minlength=self._n[a])
             ptr = np.zeros(len(counts) + 1, dtype=np.int32)
             np.cumsum(counts, out=ptr[1:])
             self._inv.append((dv.to_device(ptr, torch.int32), dv.to_device(order.astype(np.int32), torch.int32)))
@@ -189,6 +213,8 @@ class FilterConv(Module):
 
     # ---- user overrides of padded / domain values (filter.py:167-180)
     def override_padded_values(self, index, value):
+        if self._ctx.active:
+            raise NotImplementedError("FilterConv overrides address the global padded grid: not available under a slab decomposition")
         ix, iy, iz = (np.asarray(i) for i in index)
         if ix.size == 0:
             return
@@ -203,9 +229,20 @@ class FilterConv(Module):
         ex, ey, ez = np.meshgrid(xr, yr, zr, indexing="ij")
         self.override_padded_values((ex[index], ey[index], ez[index]), value)
 
+    def _extended(self, xd):
+        """This rank's layers with pz halo layers from the z-neighbours on each side (halos at the global faces are never read)."""
+        h = self._halo * self._lay
+        ext = dv.zeros(self.nel + 2 * h)
+        ext[h: h + self.nel] = xd
+        if h:
+            self._ctx.comm.exchange(ext, h, self.nel, self._lay, width=self._halo)
+        return ext
+
     def get_padded_vector(self, x):
         """Padded field on the device, flat in (z, y, x) order with x fastest."""
         xd = dv.to_device(x).reshape(-1)
+        if self._ctx.active:
+            xd = self._extended(xd)
         xpad = dv.empty(self._p[0] * self._p[1] * self._p[2])
         _lib.call("pmb_pad_gather", *self._n, *self._p, dv.ptr(self._map[0]), dv.ptr(self._map[1]), dv.ptr(self._map[2]),
                   dv.ptr(self._cval[0]), dv.ptr(self._cval[1]), dv.ptr(self._cval[2]), dv.ptr(xd), dv.ptr(xpad), dv.stream())
@@ -220,7 +257,7 @@ class FilterConv(Module):
         xpad = self.get_padded_vector(x)
         y = dv.empty(self.nel)
         k = self.weights.shape
-        _lib.call("pmb_stencil_corr", *self._p, dv.ptr(xpad), *self._n, dv.ptr(y), k[0], k[1], k[2], dv.ptr(self._w_fwd),
+        _lib.call("pmb_stencil_corr", *self._p, dv.ptr(xpad), *self._nout, dv.ptr(y), k[0], k[1], k[2], dv.ptr(self._w_fwd),
                   0, 0, 0, dv.stream())
         return dv.like_input(y, x)
 
@@ -228,12 +265,27 @@ class FilterConv(Module):
         dy = dv.to_device(dfdv).reshape(-1)
         k = self.weights.shape
         dxpad = dv.empty(self._p[0] * self._p[1] * self._p[2])
-        _lib.call("pmb_stencil_corr", *self._n, dv.ptr(dy), *self._p, dv.ptr(dxpad), k[0], k[1], k[2], dv.ptr(self._w_bwd),
+        _lib.call("pmb_stencil_corr", *self._nout, dv.ptr(dy), *self._p, dv.ptr(dxpad), k[0], k[1], k[2], dv.ptr(self._w_bwd),
                   k[0] - 1, k[1] - 1, k[2] - 1, dv.stream())
         for idx, _ in self.overrides:
             dxpad[idx] = 0.0
-        dx = dv.empty(self.nel)
+        dx = dv.empty(self._n[0] * self._n[1] * self._n[2])
         _lib.call("pmb_pad_scatter", *self._n, *self._p, dv.ptr(self._inv[0][0]), dv.ptr(self._inv[0][1]),
                   dv.ptr(self._inv[1][0]), dv.ptr(self._inv[1][1]), dv.ptr(self._inv[2][0]), dv.ptr(self._inv[2][1]),
                   dv.ptr(dxpad), dv.ptr(dx), dv.stream())
+        if self._ctx.active and self._halo:
+            # contributions that landed in my halo layers belong to the z-neighbours: send them back and add what the
+            # neighbours collected for my outermost layers (reverse of the forward halo exchange)
+            h = self._halo * self._lay
+            t = dv.zeros(4 * h)  # [lower halo | for the rank below | for the rank above | upper halo]
+            t[h: 2 * h] = dx[:h]
+            t[2 * h: 3 * h] = dx[h + self.nel:]
+            self._ctx.comm.exchange(t, h, 2 * h, self._lay, width=self._halo)
+            own = dx[h: h + self.nel].clone()
+            part = self._ctx.part
+            if part.lower is not None:
+                own[:h] += t[:h]
+            if part.upper is not None:
+                own[self.nel - h:] += t[3 * h:]
+            dx = own
         return dv.like_input(dx, dfdv)

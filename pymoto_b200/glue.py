@@ -15,6 +15,9 @@ class SIMP(Module):
     """s = xmin + (1 - xmin) * y**p"""
 
     def __init__(self, xmin=1e-9, p=3):
+        if float(p) != int(p) or int(p) < 1:
+            raise ValueError(f"pymoto_b200.SIMP evaluates integer penalisation exponents p >= 1 (got {p}); "
+                             "use the reference's MathExpression on numpy Signals for a fractional exponent")
         self.xmin, self.p = float(xmin), int(p)
 
     def __call__(self, y):
@@ -69,7 +72,9 @@ class Sum(Module):
 
             Sum._ones.clear()  # one cached vector of ones (the current problem size)
             Sum._ones[key] = torch.ones(self._n, dtype=torch.float64, device=xd.device)
-        v = dv.dots([(xd, Sum._ones[key])])[0]
+        from . import slab
+
+        v = slab.context().comm.allreduce_(dv.dots([(xd, Sum._ones[key])]))[0]  # global sum over the slabs
         return float(v.item()) if self._host else v
 
     def _sensitivity(self, dvol):

@@ -56,7 +56,7 @@ class ElemGenerator:
             lay, plane = g.nx * g.ny, (g.nx + 1) * (g.ny + 1) * g.ndof
             mask_ptr = None if self.mask is None else self.mask.data_ptr() + k_rel * plane
             flags = None
-            fv = 6 if (self.variant == 6 and g.ndof == 3) else (4 if self.variant in (4, 5) else None)
+            fv = 6 if (self.variant in (6, 7) and g.ndof == 3) else (4 if self.variant in (4, 5) else None)
             if mask_ptr is not None and g.nz > 0 and g.ndof != 2 and fv is not None:
                 flags = self._flags.get(key[:2] + (fv,))
                 if flags is None:
@@ -122,13 +122,17 @@ class DeviceCSR:
 
     # ---- vectors this operator can be applied to (halo-padded), halo refresh, global dot products
     def new_vec(self, zero=False):
-        """Owned entries of a fresh vector whose storage carries one halo node plane on each side."""
-        base = (dv.zeros if zero else dv.empty)(self.n + 2 * self.plane)
-        if not zero and self.comm is None:
-            pass  # halos are never read on one GPU (the stencil is clipped at the grid faces)
-        elif not zero:
+        """Owned entries of a fresh vector whose storage carries one halo node plane on each side (+ one node row of slack at
+        the end).  The pads are always zeroed: the bulk-copy / TMA staged matrix-free layouts read them (never using the
+        values, but they must be finite), and the first pad plane starts 16-byte aligned, which the tensor-map layout needs."""
+        row = (self.grid.nx + 1) * self.grid.ndof
+        base = dv.empty(self.n + 2 * self.plane + row + 2)
+        if zero:
+            base.zero_()
+        else:
             base[: self.plane] = 0.0
             base[self.plane + self.n:] = 0.0
+        base._pmb_padded = self.plane
         return base[self.plane: self.plane + self.n]
 
     def exchange(self, vec, lower=True, upper=True):
@@ -154,9 +158,9 @@ class DeviceCSR:
         return xp
 
     def _padded(self, x):
-        """``x`` if its storage extends at least 16 bytes on both sides (views from :meth:`new_vec` do), else a padded copy."""
+        """``x`` if it is a view made by :meth:`new_vec` (plane-padded, aligned, finite pads), else a padded copy."""
         base = x._base
-        if base is not None and x.storage_offset() >= 2 and base.numel() >= x.storage_offset() + x.numel() + 2:
+        if base is not None and getattr(base, "_pmb_padded", 0) == self.plane and x.storage_offset() == self.plane and x.numel() == self.n:
             return x
         xp = self.new_vec()
         xp.copy_(x)
@@ -170,12 +174,15 @@ class DeviceCSR:
         return d
 
     # ---- row statistics: diagonal + number of non-zero off-diagonals, one pass over the values
+    def rowstats_buffers(self):
+        if self._diag_buf is None:  # persistent storage: addresses stay fixed across updates (CUDA-graph replays rely on it)
+            self._diag_buf = dv.empty(self.n)
+            self._nnz_off_buf = dv.empty(self.n, torch.int32)
+        return self._diag_buf, self._nnz_off_buf
+
     def rowstats(self):
         if self._diag is None:
-            if self._diag_buf is None:  # persistent storage: addresses stay fixed across updates (CUDA-graph replays rely on it)
-                self._diag_buf = dv.empty(self.n)
-                self._nnz_off_buf = dv.empty(self.n, torch.int32)
-            self._diag, self._nnz_off = self._diag_buf, self._nnz_off_buf
+            self._diag, self._nnz_off = self.rowstats_buffers()
             _lib.call("pmb_rowstats", self.grid, dv.ptr(self._buf), dv.ptr(self._diag), dv.ptr(self._nnz_off), dv.stream())
         return self._diag, self._nnz_off
 

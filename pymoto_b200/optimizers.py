@@ -14,26 +14,42 @@ from . import _lib
 from . import device as dv
 
 
-def _require_single_rank(who):
-    """The design updates reduce over the design vector of THIS rank only (volume, Newton sums, step lengths): with a slab
-    decomposition every rank would take a different step.  Refuse instead of returning a wrong design."""
+def _comm():
+    """The slab communicator when the design vector is distributed over z-slabs (every rank holds its element layers and
+    the same global scalars), else None.  Only sums / maxima over the design vector cross ranks."""
     from . import slab
 
-    if slab.context().active:
-        raise NotImplementedError(f"pymoto_b200.{who}: the design update is not distributed over z-slabs yet "
-                                  "(its reductions are rank-local); gather the design on one rank or use one GPU")
+    ctx = slab.context()
+    return ctx.comm if ctx.active else None
+
+
+def _allreduce(t, op="sum"):
+    """In-place all-reduce of a small device tensor over the slabs (no-op on one GPU)."""
+    import torch.distributed as dist
+
+    comm = _comm()
+    if comm is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=comm.group)
+        comm.allreduces += 1
+    return t
+
+
+def _gnorm(v):
+    """Global 2-norm of a slab-distributed vector."""
+    return float(torch.sqrt(_allreduce((v * v).sum().reshape(1)))[0])
 
 
 class OC:
     def __init__(self, variables, response, function, move=0.1, xmin=0.0, xmax=1.0, verbosity: int = 2, l1init: float = 0.0,
                  l2init: float = 100000.0, l1l2tol: float = 1e-4, maxvol: float = None):
-        _require_single_rank("OC")
         if isinstance(variables, (list, tuple)):
             if len(variables) != 1:
                 raise NotImplementedError("pymoto_b200.OC handles one design-variable Signal")
             variables = variables[0]
         self.variable, self.response, self.function = variables, response, function
-        self.move, self.xmin, self.xmax = float(move), float(xmin), float(xmax)
+        if any(np.size(v) != 1 for v in (move, xmin, xmax)):
+            raise NotImplementedError("pymoto_b200.OC takes scalar move / xmin / xmax (vector bounds: use pymoto_b200.MMA)")
+        self.move, self.xmin, self.xmax = (float(np.asarray(v).reshape(-1)[0]) for v in (move, xmin, xmax))
         self.dx = self.xmax - self.xmin
         self.verbosity = verbosity
         self.l1init, self.l2init, self.l1l2tol, self.maxvol = l1init, l2init, l1l2tol, maxvol
@@ -43,9 +59,10 @@ class OC:
     def _update(self, x, dg):
         """xnew from x and dg (CUDA tensors): bisection of optimizers.py:425-435."""
         n = x.numel()
+        nglob = int(_allreduce(torch.tensor([float(n)], dtype=torch.float64, device=x.device))[0].item())
         if self.maxvol is None:
-            self.maxvol = float(x.sum().item()) / n
-        maxdg = float(dg.max().item())
+            self.maxvol = float(_allreduce(x.sum().reshape(1))[0].item()) / nglob
+        maxdg = float(_allreduce(dg.max().reshape(1), "max")[0].item())
         if maxdg > 1e-15:
             warnings.warn(f"OC only works for negative sensitivities: max(dgdx) = {maxdg}. Clipping positive values.")
         ws = dv.workspace().red
@@ -53,12 +70,12 @@ class OC:
         xnew = dv.empty(n)
         l1, l2 = self.l1init, self.l2init
         lmid = 0.5 * (l1 + l2)
-        target = self.maxvol * n
+        target = self.maxvol * nglob
         while l2 - l1 > self.l1l2tol:
             lmid = 0.5 * (l1 + l2)
             _lib.call("pmb_oc_candidate", n, dv.ptr(x), dv.ptr(dg), self.move, self.xmin, self.xmax, lmid, None, dv.ptr(out),
                       dv.ptr(ws), dv.stream())
-            l1, l2 = (lmid, l2) if float(out.item()) - target > 0 else (l1, lmid)
+            l1, l2 = (lmid, l2) if float(_allreduce(out).item()) - target > 0 else (l1, lmid)  # every rank takes the same branch
         _lib.call("pmb_oc_candidate", n, dv.ptr(x), dv.ptr(dg), self.move, self.xmin, self.xmax, lmid, dv.ptr(xnew), dv.ptr(out),
                   dv.ptr(ws), dv.stream())
         return xnew
@@ -66,6 +83,8 @@ class OC:
     def step(self, x=None):
         if x is not None:
             self.variable.state = x.cpu().numpy() if self._host else x
+            self.function.response()
+        elif self.response.state is None:
             self.function.response()
         g = float(self.response.state)
         self.function.reset()
@@ -91,15 +110,18 @@ class OC:
                 break
             if self.verbosity >= 2:
                 print("It. {0: 4d}, g0({1:s}): {2:+.4e}".format(self.iter, getattr(self.response, "tag", ""), g))
-            rel_step = float(torch.linalg.vector_norm((xval - xnew) / self.dx) / torch.linalg.vector_norm(xval / self.dx))
+            rel_step = _gnorm((xval - xnew) / self.dx) / _gnorm(xval / self.dx)
             if rel_step < tolx:
                 if self.verbosity >= 1:
                     print(f"OC converged: Relative stepsize |Δx|/|x| ({rel_step}) below tolerance ({tolx})")
                 break
             xval = xnew
             self.iter += 1
-        # leave the network evaluated at the last accepted design (like the reference's loop: step() sets self.x)
+        # xval is the last design the loop produced; when the loop ran out of iterations it has not been evaluated yet:
+        # evaluate it so that every Signal of the network belongs to variable.state (the reference leaves them consistent)
         self.variable.state = xval.cpu().numpy() if self._host else xval
+        if self.iter >= maxiter and self.function is not None:
+            self.function.response()
         return xval
 
 
@@ -129,6 +151,16 @@ class MmaDeviceOps:
         self.ws = dv.zeros(_lib.query("pmb_mma_ws_doubles"))
         self.out = dv.empty(16)
         self._C = C
+        # design vector distributed over z-slabs: n is this rank's share, the reduced sums / maxima are made global
+        self.n_global = int(_allreduce(torch.tensor([float(n)], dtype=torch.float64, device=self.out.device))[0].item())
+
+    def _reduce(self, nsum, nmax=0, first=0):
+        """Make out[first : first+nsum] (sums) and the nmax entries after them (maxima) global."""
+        if _comm() is not None:
+            if nsum:
+                _allreduce(self.out[first: first + nsum])
+            if nmax:
+                _allreduce(self.out[first + nsum: first + nsum + nmax], "max")
 
     def _host(self, vals):
         return (self._C.c_double * len(vals))(*[float(v) for v in vals])
@@ -157,9 +189,11 @@ class MmaDeviceOps:
         _lib.call("pmb_mma_setup", self.n, self.m, dv.ptr(xval), rows, dv.ptr(offset), self._bound(xmin), self._bound(xmax),
                   self._bound(move), float(albefa), self._host(rho), int(version), self._C.byref(self.vecs), dv.ptr(self.out),
                   dv.ptr(self.ws), dv.stream())
+        self._reduce(self.m + 1)
         return self.out[: self.m + 1].cpu().numpy()
 
     def _resid_out(self):
+        self._reduce(self.m + 1, 1)
         o = self.out[: self.m + 2].cpu().numpy()
         return float(o[0]), o[1: self.m + 1].copy(), float(o[self.m + 1])
 
@@ -172,12 +206,14 @@ class MmaDeviceOps:
         m = self.m
         _lib.call("pmb_mma_newton_sums", self.n, m, self._C.byref(self.vecs), self._host(lam), float(epsi), dv.ptr(self.out),
                   dv.ptr(self.ws), dv.stream())
+        self._reduce(2 * m + m * m)
         o = self.out[: 2 * m + m * m].cpu().numpy()
         return o[:m].copy(), o[m: 2 * m].copy(), o[2 * m:].reshape(m, m).copy()
 
     def newton_dir(self, lam, dlam, epsi):
         _lib.call("pmb_mma_newton_dir", self.n, self.m, self._C.byref(self.vecs), self._host(lam), self._host(dlam), float(epsi),
                   dv.ptr(self.out), dv.ptr(self.ws), dv.stream())
+        self._reduce(0, 4, first=1)
         return self.out[1:5].cpu().numpy()
 
     def linesearch(self, lam, steg, epsi):
@@ -265,7 +301,7 @@ def mma_design_update(ops, x, g, dg, offset, xold1, xold2, xmin, xmax, move, opt
         dg = dg + [ops.zeros(n)]
     sums = ops.setup(x, dg, offset, xmin, xmax, move, opt["albefa"], [opt["rho"]] * (m + 1), opt["version"])
     rhs = sums - g
-    epsimin_scaled = opt["epsimin"] * np.sqrt(m + n)
+    epsimin_scaled = opt["epsimin"] * np.sqrt(m + getattr(ops, "n_global", n))
     y, z, lam, mu, zet, s, its = mma_subsolv(ops, m, epsimin_scaled, opt["a0"], opt["a"], rhs[1:], opt["c"], opt["d"])
     return lam, its
 
@@ -282,7 +318,6 @@ class MMA:
     def __init__(self, variables, responses, function, slice_network=False, move=0.1, xmin=0.0, xmax=1.0, verbosity=2,
                  mmaversion="MMA2007", **kwargs):
         dv.require_cuda()
-        _require_single_rank("MMA")
         if slice_network:
             raise NotImplementedError("pymoto_b200.MMA evaluates the whole Network (slice_network=False)")
         self.variables = list(variables) if isinstance(variables, (list, tuple)) else [variables]
@@ -431,7 +466,7 @@ class MMA:
                 msgs = ["g{0:d}({1:s}): {2:+.4e}".format(i, getattr(s, "tag", ""), g[i]) for i, s in enumerate(self.responses)]
                 tag = ("[f] " if max(g[1:]) <= 0 else "[ ] ") if len(self.responses) > 1 else ""
                 print("It. {0: 4d}, {1:s}{2}".format(self.iter, tag, ", ".join(msgs)))
-            rel_stepsize = float(torch.linalg.vector_norm((xval - xnew) / self.dx) / torch.linalg.vector_norm(xval / self.dx))
+            rel_stepsize = _gnorm((xval - xnew) / self.dx) / _gnorm(xval / self.dx)
             if rel_stepsize < tolx:
                 if self.verbosity >= 1:
                     print(f"{nom} converged: Relative stepsize |Δx|/|x| ({rel_stepsize}) below tolerance ({tolx})")

@@ -109,23 +109,62 @@ class SlabComm:
         import torch.distributed._symmetric_memory as symm_mem
 
         self._cap = int(max_doubles)
-        self._mb = symm_mem.empty(4 * self._cap, dtype=torch.float64, device=device)
+        # 4 slots x 2 directions: slots 0 / 1 alternate for eagerly launched exchanges, slots 2 / 3 for exchanges captured in a
+        # CUDA graph (a replayed graph always starts on slot 2, so it can never reuse the slot of the exchange just before it)
+        self._mb = symm_mem.empty(8 * self._cap, dtype=torch.float64, device=device)
         self._mb.zero_()
+        self._symm = symm_mem
         self._hdl = symm_mem.rendezvous(self._mb, dist.group.WORLD if self.group is None else self.group)
         p = self.part
-        self._peer_lo = self._hdl.get_buffer(p.lower, (4 * self._cap,), torch.float64) if p.lower is not None else None
-        self._peer_hi = self._hdl.get_buffer(p.upper, (4 * self._cap,), torch.float64) if p.upper is not None else None
+        self._peer_lo = self._hdl.get_buffer(p.lower, (8 * self._cap,), torch.float64) if p.lower is not None else None
+        self._peer_hi = self._hdl.get_buffer(p.upper, (8 * self._cap,), torch.float64) if p.upper is not None else None
         self._slot = 0
+        self._gslot = 0
         self.fast = True
         return True
+
+    # ---- CUDA-graph capture of code that exchanges halos (the slab V-cycle)
+    def begin_capture(self):
+        self._gslot = 0
+
+    def end_capture(self):
+        """Last captured operation: one more barrier, so that two back-to-back replays (last exchange of one, first of the
+        next) are separated like any two exchanges on different slots are."""
+        if self.fast:
+            self._hdl.barrier(channel=0)
+
+    def symmetric_vector(self, n):
+        """A zeroed float64 vector in symmetric memory and the views of every rank's copy (for :meth:`bcast_part`)."""
+        buf = self._symm.empty(int(n), dtype=torch.float64, device=self._mb.device)
+        buf.zero_()
+        hdl = self._symm.rendezvous(buf, dist.group.WORLD if self.group is None else self.group)
+        peers = [hdl.get_buffer(r, (int(n),), torch.float64) for r in range(self.part.world)]
+        return buf, peers, hdl
+
+    def bcast_part(self, local, peers, hdl, offset):
+        """Replicate a distributed vector without a collective: every rank stores its part at ``offset`` of every rank's
+        copy (peer stores over NVLink), one device-side barrier completes the vector everywhere.  Deterministic, capturable."""
+        from . import _lib
+
+        st = torch.cuda.current_stream().cuda_stream
+        n, src = local.numel(), local.data_ptr()
+        dsts = [p.data_ptr() + 8 * offset for p in peers]
+        for i in range(0, len(dsts), 2):
+            _lib.call("pmb_halo_copy2", n, src, dsts[i], src if i + 1 < len(dsts) else None, dsts[i + 1] if i + 1 < len(dsts) else None, st)
+        hdl.barrier(channel=0)
+        self.allreduces += 1
 
     def _fast_exchange(self, base, own_offset, own_len, n, lower, upper):
         from . import _lib
 
         p = self.part
         st = torch.cuda.current_stream().cuda_stream
-        o = (self._slot & 1) * 2 * self._cap
-        self._slot += 1
+        if torch.cuda.is_current_stream_capturing():
+            o = (2 + (self._gslot & 1)) * 2 * self._cap
+            self._gslot += 1
+        else:
+            o = (self._slot & 1) * 2 * self._cap
+            self._slot += 1
         b0 = base.data_ptr() + 8 * own_offset  # first owned entry
         # box layout per slot: [0, cap) = planes coming from the rank below, [cap, 2 cap) = from the rank above
         # `upper` = I want my upper halo filled = every rank sends its bottom planes down; `lower` = top planes go up
@@ -274,8 +313,12 @@ def reset():
 
 
 def context(nz=None, n_levels=1):
-    """The active context, or a trivial single-rank one."""
+    """The active context, or a trivial single-rank one.  ``nz`` (when given) must be the z-size the active decomposition
+    was made for: a module built on another domain would silently use the wrong slab."""
     if _context is not None:
+        if nz is not None and _context.active and int(nz) != _context.part.nz:
+            raise ValueError(f"active slab decomposition is for nz = {_context.part.nz}, module domain has nz = {nz}; "
+                             "call pymoto_b200.slab.init(domain, ...) for this domain (or slab.reset())")
         return _context
     part = SlabPartition(nz or 0, 1, 0, n_levels=n_levels)
     return SlabContext(part, SlabComm(part))

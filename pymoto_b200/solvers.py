@@ -137,6 +137,8 @@ class SolverDenseInverse(LinearSolver):
 
     def solve(self, rhs, x0=None, trans="N"):
         _check_trans(trans)
+        if not self._checked and not torch.cuda.is_current_stream_capturing():
+            self._check_info()  # first solve after an update: a non-positive pivot must not go unnoticed (the reference pivots)
         r = dv.to_device(rhs).reshape(-1)
         out = self._out if dv.is_device(rhs) else dv.empty(self.n)
         _lib.call("pmb_dense_gemv", self.n, dv.ptr(self.inv), dv.ptr(r), dv.ptr(out), dv.stream())
@@ -160,6 +162,9 @@ class GeometricMultigrid(Preconditioner):
     # fine matrix comes from an assembly module (3-D): the fine values are not read and no intermediate is written.
     # PMB_GALERKIN_DIRECT=0 keeps the generic two-pass product R^T (A R) on every level.
     direct_level1 = os.environ.get("PMB_GALERKIN_DIRECT", "1") != "0"
+    # Capture the V-cycle of a slab-decomposed hierarchy as well (needs the symmetric-memory mailboxes: the halo copies, the
+    # device-side barriers and the peer-store gather of the first replicated level are ordinary stream work).
+    graph_on_slabs = os.environ.get("PMB_GRAPH_SLABS", "1") != "0"
 
     def __init__(self, domain, A=None, cycle: str = "V", inner_level: LinearSolver = None, smoother: LinearSolver = None,
                  smooth_steps: int = 5):
@@ -181,6 +186,8 @@ class GeometricMultigrid(Preconditioner):
         self._replicate = False
         self._graph = None
         self._graph_sig = None
+        self._graph_failed = False
+        self._rc_sym = None
         self._eager_calls = 0
         super().__init__(A)
 
@@ -259,7 +266,15 @@ class GeometricMultigrid(Preconditioner):
                 self._coarse_entry_offset = 0 if k0c == 0 else _lib.query(
                     "pmb_nnz", make_grid(nx // 2, ny // 2, nz // 2, g.ndof, 0, k0c))
                 self._coarse_row_offset = k0c * self.Ac.plane
-                self._rc_full = dv.empty(self.Ac.shape[0])
+                self._rc_sym = None
+                if A.comm.fast and os.environ.get("PMB_SYMM_GATHER", "1") != "0":
+                    try:  # replicated right-hand side assembled by peer stores (no collective, capturable in a CUDA graph)
+                        self._rc_full, peers, hdl = A.comm.symmetric_vector(self.Ac.shape[0])
+                        self._rc_sym = (peers, hdl)
+                    except Exception as e:
+                        warnings.warn(f"symmetric-memory gather unavailable ({e}); using the NCCL all-reduce")
+                if self._rc_sym is None:
+                    self._rc_full = dv.empty(self.Ac.shape[0])
             else:
                 self.Ac = self._Ac_local = DeviceCSR(self._gc_local, comm=A.comm, level=A.level + 1)
         nc_local = _lib.query("pmb_nrows", self._gc_local)
@@ -269,45 +284,78 @@ class GeometricMultigrid(Preconditioner):
         """Addresses of everything a captured V-cycle reads or writes, down the whole hierarchy."""
         sig, lvl = [], self
         while isinstance(lvl, GeometricMultigrid):
-            if lvl.A is None or lvl._buf is None or lvl.A.comm is not None:
+            if lvl.A is None or lvl._buf is None:
                 return None
+            if lvl.A.comm is not None and not (lvl.A.comm.fast and GeometricMultigrid.graph_on_slabs
+                                               and (not lvl._replicate or lvl._rc_sym is not None)):
+                return None  # slab levels are capturable only with mailbox halos and the peer-store gather
             gen = lvl.A.generator if DeviceCSR.matrix_free else None
             sig += [lvl.A._buf.data_ptr(), lvl.smoother.D.data_ptr(), float(lvl.smoother.w), lvl.smooth_steps,
                     None if gen is None else (gen["s"].data_ptr(), None if gen["mask"] is None else gen["mask"].data_ptr(),
                                               gen["bcdiag"], gen["ke"].ctypes.data, gen["ke"].tobytes(), gen.variant)]
             sig += [lvl._buf[k].data_ptr() for k in ("u", "u2", "t", "rc")]
+            sig += [lvl.A.grid.kz0, lvl.A.grid.nzl, lvl._replicate]
             lvl = lvl.inner_level
         if not isinstance(lvl, SolverDenseInverse) or lvl.inv is None:
             return None
         return tuple(sig + [lvl.inv.data_ptr(), lvl._out.data_ptr(), lvl.n])
 
+    def _coarsest(self):
+        lvl = self
+        while isinstance(lvl, GeometricMultigrid):
+            lvl = lvl.inner_level
+        return lvl if isinstance(lvl, SolverDenseInverse) else None
+
     def solve(self, rhs, x0=None, trans="N"):
         _check_trans(trans)
+        if self.A is not None and self.A.level == 0 and not torch.cuda.is_current_stream_capturing():
+            inner = self._coarsest()  # graph replays never pass through SolverDenseInverse.solve: check the pivots here
+            if inner is not None and inner.inv is not None and not inner._checked:
+                inner._check_info()
         if (GeometricMultigrid.use_cuda_graph and x0 is None and dv.is_device(rhs) and self.A is not None
-                and self.A.comm is None and self.A.level == 0 and rhs.numel() == self.A.shape[0]
+                and self.A.level == 0 and rhs.numel() == self.A.shape[0] and not self._graph_failed
                 and not torch.cuda.is_current_stream_capturing()):
             sig = self._signature()
             if sig is not None:
                 if self._graph is not None and sig != self._graph_sig:
-                    self._graph = None
+                    self._graph, self._eager_calls = None, 0  # re-measure the launch statistics with one eager pass, then re-capture
                 if self._graph is None and self._eager_calls >= 1:  # one eager pass first (lazy kernel attributes etc.)
+                    comm = self.A.comm
                     self._graph_in = dv.empty(self.A.shape[0])
                     self._graph_in.copy_(rhs.reshape(-1))
                     torch.cuda.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._graph_out = self._solve_eager(self._graph_in, None)
-                    self._graph, self._graph_sig = g, self._signature()
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        if comm is not None:  # every rank captures the same V-cycle, mailbox exchanges and barriers included
+                            comm.barrier()
+                            comm.begin_capture()
+                        with torch.cuda.graph(g):
+                            self._graph_out = self._solve_eager(self._graph_in, None)
+                            if comm is not None:
+                                comm.end_capture()
+                        self._graph, self._graph_sig = g, self._signature()
+                    except Exception as e:  # e.g. a symmetric-memory barrier that cannot be captured on this build
+                        if comm is None:
+                            raise
+                        warnings.warn(f"slab V-cycle could not be captured into a CUDA graph ({e}); running it eagerly")
+                        self._graph, self._graph_failed = None, True
+                        torch.cuda.synchronize()
                 if self._graph is not None:
                     self._graph_in.copy_(rhs.reshape(-1))
                     self._graph.replay()
                     _lib.launch_count += self._graph_launches  # the replay launches the same kernels as the eager pass
                     for key, cnt in self._graph_stats.items():
                         _lib.call_stats[key] = _lib.call_stats.get(key, 0) + cnt
+                    if self.A.comm is not None:
+                        self.A.comm.exchanges += self._graph_comm[0]
+                        self.A.comm.allreduces += self._graph_comm[1]
                     return self._graph_out
         self._eager_calls += 1
         n0, s0 = _lib.launch_count, dict(_lib.call_stats)
+        c0 = (self.A.comm.exchanges, self.A.comm.allreduces) if self.A is not None and self.A.comm is not None else (0, 0)
         out = self._solve_eager(rhs, x0)
+        if self.A is not None and self.A.comm is not None:
+            self._graph_comm = (self.A.comm.exchanges - c0[0], self.A.comm.allreduces - c0[1])
         self._graph_launches = _lib.launch_count - n0
         self._graph_stats = {k: c - s0.get(k, 0) for k, c in _lib.call_stats.items() if c - s0.get(k, 0) > 0}
         return out
@@ -331,7 +379,10 @@ class GeometricMultigrid(Preconditioner):
         A.exchange(t, lower=True, upper=False)  # restriction of coarse plane K reads fine planes 2K-1 .. 2K+1
         _lib.call("pmb_restrict", A.grid, self._gc_local, dv.ptr(t), dv.ptr(rc), st)
         if self._replicate:
-            A.comm.gather_full(rc, self._rc_full, self._coarse_row_offset)
+            if self._rc_sym is not None:
+                A.comm.bcast_part(rc, self._rc_sym[0], self._rc_sym[1], self._coarse_row_offset)
+            else:
+                A.comm.gather_full(rc, self._rc_full, self._coarse_row_offset)
             uc_full = self.inner_level.solve(self._rc_full)
             uc_ptr = uc_full.data_ptr() + 8 * self._coarse_row_offset  # the slab view includes its upper halo plane
         else:
@@ -514,6 +565,9 @@ class CG(LinearSolver):
                 print(f"CG i = {i}, residuals = {tval}")
             if tval <= self.tol:
                 break
+            if not np.isfinite(tval):
+                raise np.linalg.LinAlgError(f"CG residual became {tval} in iteration {i} (singular or indefinite operator / "
+                                            "preconditioner, e.g. no Dirichlet condition)")
             z = M.solve(r, trans="N")
             qz = A.dots([(q, z)])
             # p = z + beta p, beta = -(q.z)/(p.q)

@@ -93,10 +93,126 @@ def main():
         assert err_dx <= 1e-6, err_dx
         assert abs(cg.iterations - P.cg.iterations) <= 1
         pmb.slab.reset()
+    design_updates(rank, world)
+    filterconv_slabs(rank, world)
     dist.barrier()
     if rank == 0:
         print("[dist_check] OK")
     dist.destroy_process_group()
+
+
+def filterconv_slabs(rank, world):
+    """FilterConv (the filter of examples/topology_optimization/ex_compliance_multigrid.py:83) on z-slabs: forward and
+    backward against the oracle on the whole grid, symmetric / edge / constant z-faces, radius 2 and 3.2."""
+    import pymoto_b200 as pmb
+    from pymoto_b200 import device as dv
+    from oracle import Grid
+    from oracle.nextrows import FilterConv as OracleFilterConv
+
+    nx, ny, nz = 9, 7, 6 * world
+    gr = Grid(nx, ny, nz)
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    ctx = pmb.slab.init(dom, n_levels=1)
+    e0, e1 = ctx.part.elem_layers(0)
+    lay = nx * ny
+    rng = np.random.default_rng(21)
+    x, dy = rng.random(gr.nel), rng.standard_normal(gr.nel)
+    for kw in (dict(radius=2.0), dict(radius=3.2, zmin_bc="edge", zmax_bc=0.25), dict(radius=2.0, xmin_bc="wrap", xmax_bc="wrap", zmax_bc="edge")):
+        ref = OracleFilterConv(gr, **kw)
+        y_ref, dx_ref = ref(x.copy()), ref.sensitivity(dy.copy(), gr.nel)
+        flt = pmb.FilterConv(dom, **kw)
+        y = flt(dv.to_device(x[e0 * lay:e1 * lay].copy()))
+        dx = flt._sensitivity(dv.to_device(dy[e0 * lay:e1 * lay].copy()))
+        ey = np.abs(y.cpu().numpy() - y_ref[e0 * lay:e1 * lay]).max()
+        ed = np.abs(dx.cpu().numpy() - dx_ref[e0 * lay:e1 * lay]).max()
+        assert ey <= 1e-12 and ed <= 1e-12, ("FilterConv slab", kw, ey, ed)
+    if rank == 0:
+        print(f"[dist_check] FilterConv on {world} slabs: forward / backward match the oracle to 1e-12 (3 boundary sets)")
+    pmb.slab.reset()
+
+
+def design_updates(rank, world):
+    """Three OC and three MMA design updates with the design vector distributed over the slabs (volume sum, Newton sums,
+    maxima and step lengths all-reduced) against the numpy oracle on the whole grid: designs agree to 1e-6 / 1e-5, responses
+    to 1e-6 relative."""
+    import pymoto_b200 as pmb
+    from pymoto_b200 import device as dv
+    from oracle import Grid
+    from oracle.chain import ComplianceProblem
+    from oracle.nextrows import MMAOracle, oc_update
+
+    nx, ny, nz = 16, 8, 8 * world
+    gr = Grid(nx, ny, nz)
+    P = ComplianceProblem(gr, kind="cantilever", tol=1e-10, min_size=4)
+    n = gr.nel
+    # ---- oracle histories
+    x = np.full(n, 0.5)
+    oc_hist = []
+    for _ in range(3):
+        c = P.response(x)
+        x = oc_update(x, P.sensitivity())
+        oc_hist.append((c, x.copy()))
+    P.u = None
+    x = np.full(n, 0.5)
+    mo, sf, mma_hist = MMAOracle(n, 2), None, []
+    for _ in range(3):
+        c = P.response(x)
+        sf = 100.0 / abs(c) if sf is None else sf
+        g = np.array([c * sf, (P.y.sum() - 0.5 * n) / (0.5 * n) * 10.0])
+        dvol = P.filt.sensitivity(np.full(n, 10.0 / (0.5 * n)))
+        x = mo.step(x, g, np.vstack([P.sensitivity() * sf, dvol]))
+        mma_hist.append((g, x.copy()))
+
+    # ---- the same loops on the slabs
+    dom = pmb.VoxelDomain(nx, ny, nz)
+
+    def network(with_volume):
+        mgs = pmb.solvers.auto_multigrid(dom, min_size=4)
+        ctx = pmb.slab.init(dom, n_levels=len(mgs) + 1, min_planes=2, min_dofs=0)
+        k0, k1 = ctx.part.planes(0)
+        e0, e1 = ctx.part.elem_layers(0)
+        plane, lay = (nx + 1) * (ny + 1) * 3, nx * ny
+        f = dv.to_device(P.f[k0 * plane:k1 * plane].copy())
+        sx = pmb.Signal("x", state=dv.to_device(np.full((e1 - e0) * lay, 0.5)))
+        with pmb.Network() as fn:
+            sy = pmb.DensityFilter(dom, radius=2.0)(sx)
+            ss = pmb.SIMP(1e-9, 3)(sy)
+            sK = pmb.AssembleStiffness(dom, bc=P.bc)(ss)
+            su = pmb.LinSolve(hermitian=True, solver=pmb.solvers.CG(preconditioner=mgs[0], tol=1e-10))(sK, f)
+            sc = pmb.Compliance()(su, f)
+            if with_volume:
+                sg0 = pmb.Scaling(scaling=100.0)(sc)
+                sg1 = pmb.Scaling(scaling=10.0, maxval=0.5 * n)(pmb.Sum()(sy))
+        return sx, ([sg0, sg1] if with_volume else sc), fn, (e0 * lay, e1 * lay)
+
+    def gathered(xloc):
+        parts = [torch.empty_like(xloc) for _ in range(world)]
+        dist.all_gather(parts, xloc.contiguous())
+        return torch.cat(parts).cpu().numpy()
+
+    sx, sc, fn, _ = network(False)
+    oc = pmb.OC(sx, sc, fn, verbosity=0)
+    xl = None
+    for it, (c_ref, x_ref) in enumerate(oc_hist):
+        xl, g, _ = oc.step(xl)
+        xg = gathered(xl)
+        assert abs(g - c_ref) <= 1e-6 * abs(c_ref), ("OC objective", it, g, c_ref)
+        assert np.abs(xg - x_ref).max() <= 1e-6, ("OC design", it, np.abs(xg - x_ref).max())
+    if rank == 0:
+        print(f"[dist_check] OC on {world} slabs: 3 updates match the oracle (|dx| <= 1e-6), last objective {g!r}")
+    pmb.slab.reset()
+
+    sx, resp, fn, _ = network(True)
+    mma = pmb.MMA(sx, resp, fn, verbosity=0)
+    xl = None
+    for it, (g_ref, x_ref) in enumerate(mma_hist):
+        xl, g, _ = mma.step(xl)
+        xg = gathered(xl)
+        np.testing.assert_allclose(np.asarray(g, dtype=float), g_ref, rtol=1e-6, atol=1e-8)
+        assert np.abs(xg - x_ref).max() <= 1e-5, ("MMA design", it, np.abs(xg - x_ref).max())
+    if rank == 0:
+        print(f"[dist_check] MMA on {world} slabs: 3 updates match the oracle (|dx| <= 1e-5), Newton iterations {mma.newton_iterations}")
+    pmb.slab.reset()
 
 
 if __name__ == "__main__":

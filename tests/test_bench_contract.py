@@ -1,5 +1,6 @@
-"""bench.py contract on CPU: the reference arm (oracle port timed on the host cores) prints exactly one JSON line with
-the keys the driver reads, and non-zero ranks of a multi-rank launch do no work."""
+"""bench.py contract on CPU: the reference arm (the unmodified reference timed on the host cores; the oracle port only when
+the reference cannot be imported) prints exactly one JSON line with the keys the driver reads, and non-zero ranks of a
+multi-rank launch do no work."""
 import json
 import os
 import subprocess
@@ -23,8 +24,14 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "design_iters_per_sec" and d["unit"] == "iter/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
-    assert "oracle port" in d["cpu_baseline"]["sample"]
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import refload
+
+    have_ref = refload.reference_root() is not None
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert ("UNMODIFIED pyMOTO" if have_ref else "oracle port") in d["cpu_baseline"]["sample"]
+    assert d["config"]["same_config"] is False and d["config"]["extrapolation_factor"] >= 1.0
     assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
 

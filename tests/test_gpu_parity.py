@@ -437,6 +437,50 @@ def test_golden_compliance_64x32x32(pmb):
     assert torch.allclose(flt(x + x2), flt(x) + flt(x2), rtol=1e-13, atol=1e-13)
 
 
+def test_dropin_under_real_pymoto_runtime():
+    """INTEGRATION.md section 3 verbatim under the unmodified reference's own Module / Network runtime and MMA optimiser
+    (fresh interpreter: pymoto must be importable BEFORE pymoto_b200 so that the hot-path classes derive from pymoto.Module)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "baseline"))
+    import refload
+
+    if refload.reference_root() is None:
+        pytest.skip("reference not installed (python baseline/install_ref.py)")
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "dropin_check.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "[dropin_check] OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_pure_c_abi_solve_without_torch():
+    """A host with no torch in the process (cudaMalloc through ctypes) builds the multigrid hierarchy and solves 32x16x16 with
+    pmb_pcg_solve through the C ABI alone; iterations, residual and solution against the oracle."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "c_abi_check.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "[c_abi_check] OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_c_abi_comm_entry_points_two_gpus(tmp_path):
+    """pmb_comm_init / pmb_halo_exchange / pmb_allreduce (NCCL bound at run time) from two plain processes, one per GPU."""
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    idfile = str(tmp_path / "nccl_id.bin")
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "c_abi_check.py"), "comm", str(r), "2", idfile],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"comm rank {r}/2 OK" in o, o[-3000:]
+
+
 def test_multi_gpu_slab_parity():
     """z-slab path on 2 GPUs vs the oracle (skipped on a single-GPU box; run with `gpurun --gpus 2`)."""
     import os
@@ -492,7 +536,7 @@ def test_matrix_free_operator_equals_assembled(pmb, shape, ndof):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,ndof", [((37, 9, 7), 3), ((33, 6, 4), 3), ((40, 7, 6), 1), ((64, 32, 32), 3), ((5, 20, 19), 3), ((34, 9, 17), 2),
-                                        ((66, 16, 5), 3), ((31, 8, 2), 3)])
+                                        ((66, 16, 5), 3), ((31, 8, 4), 3)])
 def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     """Every layout of the 3-D matrix-free kernel must reproduce variant 0 (one node per thread on a brick): the z-marching
     columns (1, 2) and the bulk-copy ring layouts (4, 5; with and without brick flags) bit for bit, the FP64 tensor-core layout (3; DMMA accumulation order) to 1e-11 of the field magnitude in y (same products, same order per node) for all modes, on the whole grid and
@@ -519,14 +563,14 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
     try:
         ref = {}
         nvar = _lib.query("pmb_elem_num_variants")
-        assert nvar >= 7
+        assert nvar >= 8
         for variant in range(nvar):
             gen.variant = variant
             for mode in (_lib.SPMV, _lib.RESIDUAL, _lib.JACOBI):
                 out, d3 = dv.zeros(n), dv.empty(3)
                 K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
                 got = (out.cpu().numpy(), d3.cpu().numpy())
-                exact = variant not in (3, 6) or ndof != 3
+                exact = variant not in (3, 6, 7) or ndof != 3
                 if variant == 0:
                     ref[mode] = got
                 elif exact:
@@ -551,7 +595,7 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
                 assert np.array_equal(got, want), ("slab", variant)
             else:
                 np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * max(1.0, np.abs(want).max()))
-            if variant in (4, 5, 6):  # without brick flags every brick applies the mask: same result
+            if variant in (4, 5, 6, 7):  # without brick flags every brick applies the mask: same result
                 op = gen.op()
                 bare = _lib.ElemOp(op.Ke_host, op.s, op.bcmask, op.bcdiagval, None, variant)
                 out = dv.zeros(n)
@@ -570,7 +614,7 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
                       fscr.data_ptr(), allow, C.addressof(ms), C.byref(best), dv.stream())
             assert all(0.0 < t < 1e3 for t in ms)
             assert 0 <= best.value < nvar
-        assert best.value not in (3, 6) or ndof != 3
+        assert best.value not in (3, 6, 7) or ndof != 3
         np.testing.assert_allclose(scratch.cpu().numpy(), ref[_lib.JACOBI][0], rtol=0, atol=1e-11 * max(1.0, np.abs(ref[_lib.JACOBI][0]).max()))
     finally:
         gen.variant = saved
