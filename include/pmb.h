@@ -112,7 +112,7 @@ long long pmb_ws_doubles(void);
  * caller-owned POD (no state is kept in the library):
  *   Ke_host     (nn*ndof)^2 row-major, HOST pointer (passed to the kernel through the parameter constant bank)
  *   s, bcmask   DEVICE pointers (bcmask: 1 byte per dof, may be NULL); bcdiagval: diagonal of the Dirichlet rows
- *   brickflags  optional DEVICE bytes from pmb_elem_brickflags (layouts 4 - 6 skip all Dirichlet-mask traffic in bricks whose
+ *   brickflags  optional DEVICE bytes from pmb_elem_brickflags (layouts 4 - 7 skip all Dirichlet-mask traffic in bricks whose
  *               flag is 0; NULL = every brick checks the mask)
  *   variant     kernel layout, 0 .. pmb_elem_num_variants()-1 (3-D, ndof 1 or 3; everything else runs layout 0):
  *               0 = one node per thread on a 32x4x2 brick, 1 / 2 = z-marching 32x8 / 32x4 columns with ring-buffered
@@ -135,7 +135,7 @@ int pmb_elem_spmv(const pmb_grid* g, int mode, const pmb_elem_op* op, const doub
                   double w, double* y, const double* dotv, double* dot_out, double* ws, void* stream);
 long long pmb_elem_ws_doubles(const pmb_grid* g);
 int pmb_elem_num_variants(void);
-/* flags[unit] = 1 iff the region of the slab that layout `variant` (4, 5: a 32x4x2-node brick + 1-node apron; 6: one
+/* flags[unit] = 1 iff the region of the slab that layout `variant` (0, 4, 5: a 32x4x2-node brick + 1-node apron; 6, 7: one
  * 8-row step of a 32x2 node-column strip) stages for that unit of work holds a masked dof; pmb_elem_brickflags_bytes(g,
  * variant) bytes.  Computed once per bc set, slab and layout. */
 long long pmb_elem_brickflags_bytes(const pmb_grid* g, int variant);

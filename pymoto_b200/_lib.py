@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmb.so")
+LIB_PATH = os.environ.get("PMB_LIB_PATH", os.path.join(_HERE, "libpmb.so"))  # PMB_LIB_PATH: diagnostic builds only
 
 
 class PmbError(RuntimeError):

@@ -26,7 +26,8 @@ struct KeParam {
 
 template <int NDOF, bool DIM3, int MODE>
 __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_constant__ KeParam<NDOF, DIM3> ke, const double* __restrict__ s,
-                                                    const unsigned char* __restrict__ mask, double bcdiag,
+                                                    const unsigned char* __restrict__ mask_in,
+                                                    const unsigned char* __restrict__ flags, double bcdiag,
                                                     const double* __restrict__ x, const double* __restrict__ b,
                                                     const double* __restrict__ diag, double w, double* __restrict__ y,
                                                     const double* __restrict__ dotv, double* __restrict__ partials) {
@@ -40,6 +41,10 @@ __global__ void __launch_bounds__(256, 3) elem_kernel(Geo g, const __grid_consta
 
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY, kl0 = blockIdx.z * BZ;  // kl0: plane index relative to kz0
+  // (brick flags are NOT used here: reading the flag first puts one more dependent global load in front of the staging loads
+  //  of every CTA and costs more than the mask bytes it saves -- measured 0.363 vs 0.348 ms at 256x128x128)
+  const unsigned char* mask = mask_in;
+  (void)flags;
 
   // ---- stage the masked input vector of the brick + 1-node apron (zero outside the grid).  A (tz, ty) row of the
   //      brick is TX*NDOF contiguous doubles of x: two rows per pass, 128 threads each, no per-element index division
@@ -962,19 +967,25 @@ __global__ void __launch_bounds__(256) elem_brickflags_kernel(Geo g, int nbx, in
 // Staging is the bulk-copy ring of the layouts above (per step 36 node rows + 24 density rows, one per lane of warp 0).
 // Tensor-core accumulation order differs from the DFMA layouts: y agrees to rounding, not bit for bit.
 // ---------------------------------------------------------------------------------------------------------
+#ifndef PMB_YM_DBG
+#define PMB_YM_DBG 0   // diagnostic builds only (scripts/ablate_ym.sh): 1 = no epilogue, 2 = no DMMA, 4 = no shared loads, 8 = no finalize
+#endif
 struct YmCfg {
   static constexpr int BX = 32, BZ = 2, JB = 8, NT = 256, NDOF = 3;
   static constexpr int XLEN = (BX + 2) * NDOF;               // doubles of a staged node row (34 nodes)
   static constexpr int XROWS = (BZ + 2) * (JB + 1);          // node rows a step needs: 4 planes x 9 rows
   // tensor-map TMA staging: per plane two boxes of 5 rows x 102 doubles (rows of even / odd parity, see below), each
   // padded to 512 doubles (4096 B); one box of 34 x 8 x 3 element densities
-  static constexpr int XBOX_ROWS = 5, XREG = 512, XDOUBLES = (BZ + 2) * 2 * XREG;
-  static constexpr int SBOX_X = BX + 2, SDOUBLES = SBOX_X * JB * (BZ + 1);
+  // (a TMA box must START on a 16-byte boundary -- an odd double coordinate traps with "illegal instruction",
+  //  scripts/probe_tma_f64.cu -- so boxes start one double / one element early where needed and are 104 / 36 wide)
+  static constexpr int XBOX_ROWS = 5, XBOX = XLEN + 2, XREG = 528, XDOUBLES = (BZ + 2) * 2 * XREG;
+  static constexpr int SBOX_X = BX + 4, SDOUBLES = SBOX_X * JB * (BZ + 1);
   static constexpr int STAGE = XDOUBLES + SDOUBLES, STAGES = 2;
   static constexpr int OUTW = 8 * NDOF;                      // outputs of a warp per node row
   static constexpr int SMEM_DOUBLES = STAGE * STAGES + (NT / 32) * (JB * OUTW + OUTW) + 24 * 24;
-  static_assert(XBOX_ROWS * XLEN <= XREG && (XREG * 8) % 128 == 0 && (STAGE * 8) % 128 == 0, "TMA boxes land 128-byte aligned");
-  static_assert((XLEN * 8) % 16 == 0 && (SBOX_X * 8) % 16 == 0, "TMA box rows are whole 16-byte granules");
+  static_assert(XBOX_ROWS * XBOX <= XREG && (XREG * 8) % 128 == 0 && (XDOUBLES * 8) % 128 == 0 && (STAGE * 8) % 128 == 0,
+                "TMA boxes land 128-byte aligned");
+  static_assert((XBOX * 8) % 16 == 0 && (SBOX_X * 8) % 16 == 0, "TMA box rows are whole 16-byte granules");
 };
 
 // TMA tensor-map loads (cp.async.bulk.tensor, SASS UTMALDG): coordinates are ELEMENT indices, innermost first; the part of
@@ -994,13 +1005,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 template <int MODE, int CTAS>
 __global__ void __launch_bounds__(YmCfg::NT, CTAS)
-    elem_kernel_ym(Geo g, const __grid_constant__ KeParam<3, true> ke, const __grid_constant__ CUtensorMap tmx,
-                   const __grid_constant__ CUtensorMap tms, int nsteps, int skew, int szoff,
+    elem_kernel_ym(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tms, Geo g,
+                   const __grid_constant__ KeParam<3, true> ke, int nsteps, int nbz, int szoff,
                    const unsigned char* __restrict__ mask, const unsigned char* __restrict__ flags, double bcdiag,
                    const double* __restrict__ x, const double* __restrict__ b, const double* __restrict__ diag, double w,
                    double* __restrict__ y, const double* __restrict__ dotv, double* __restrict__ partials) {
   using C = YmCfg;
-  constexpr int NDOF = 3, JB = C::JB, NT = C::NT, XL = C::XLEN, XREG = C::XREG;
+  constexpr int NDOF = 3, JB = C::JB, NT = C::NT, XL = C::XBOX, XREG = C::XREG;
   extern __shared__ __align__(128) double ring[];
   double* sOut = ring + C::STAGE * C::STAGES;                 // [warp][JB][24] finished rows, then [warp][24] carry
   double* sCarry = sOut + (NT / 32) * JB * C::OUTW;
@@ -1010,7 +1021,10 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
   __shared__ double wred[3][NT / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i0 = blockIdx.x * C::BX, kl0 = blockIdx.y * C::BZ;
+  // 1-D grid, strip-major: the CTAs of strip 0 (the ones that usually carry the Dirichlet face and patch their stages) start
+  // in the first wave, the nearly empty last strip runs last
+  const int bxs = blockIdx.x / nbz, bzs = blockIdx.x - bxs * nbz;
+  const int i0 = bxs * C::BX, kl0 = bzs * C::BZ;
   if (tid < C::STAGES) done_cnt[tid] = 0;
   const long long xrow = (long long)g.NX * NDOF;
 
@@ -1024,6 +1038,8 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
+  // (the tensor maps are the FIRST kernel parameters: a descriptor that sits beyond the classic 4 KB parameter window --
+  //  behind the 4.6 KB element matrix -- makes cp.async.bulk.tensor trap with "illegal instruction")
   // ---- producer (one thread): 8 + 1 tensor-map TMA loads per step instead of 60 row copies (the copy engine retires only
   //      ~10 small bulk copies per microsecond and SM, which capped every row-staged layout at ~0.4 ms).
   //      Node vector: a row of nodes is NX*3 doubles -- an odd number, so neither the row nor the plane stride is a multiple
@@ -1040,7 +1056,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
 #pragma unroll
     for (int p = 0; p < C::BZ + 2; ++p) {
       const int klp = kl0 - 1 + p, k = g.kz0 + klp;
-      if (k >= 0 && k < g.NZ && klp <= g.nzl) bytes += 2u * C::XBOX_ROWS * XL * 8u;
+      if (k >= 0 && k < g.NZ && klp <= g.nzl) bytes += 2u * C::XBOX_ROWS * XL * 8u;  // full boxes count, zero-filled parts included
     }
     mbar_expect_tx(&full_bar[stg], bytes);
 #pragma unroll
@@ -1048,11 +1064,12 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
       const int klp = kl0 - 1 + p, k = g.kz0 + klp;
       if (k >= 0 && k < g.NZ && klp <= g.nzl) {   // planes outside the grid / beyond the upper halo stay zero
         const int R0 = (klp + 1) * g.NY + JB * t2, a = R0 & 1;   // row index in the map (its first plane is local plane -1)
-        tma_load_2d(su + (2 * p) * XREG, &tmx, a * (int)xrow + (i0 - 1) * NDOF, R0 >> 1, &full_bar[stg]);
-        tma_load_2d(su + (2 * p + 1) * XREG, &tmx, (1 - a) * (int)xrow + (i0 - 1) * NDOF, (R0 + 1) >> 1, &full_bar[stg]);
+        // box starts floored to an even double: the wanted first double then sits at offset (start & 1) of every box row
+        tma_load_2d(su + (2 * p) * XREG, &tmx, (a * (int)xrow + (i0 - 1) * NDOF) & ~1, R0 >> 1, &full_bar[stg]);
+        tma_load_2d(su + (2 * p + 1) * XREG, &tmx, ((1 - a) * (int)xrow + (i0 - 1) * NDOF) & ~1, (R0 + 1) >> 1, &full_bar[stg]);
       }
     }
-    tma_load_3d(su + C::XDOUBLES, &tms, i0 - 1, JB * t2, kl0 - 1 + szoff, &full_bar[stg]);
+    tma_load_3d(su + C::XDOUBLES, &tms, i0 - 2, JB * t2, kl0 - 1 + szoff, &full_bar[stg]);
   };
   if (tid == 0)
     for (int t2 = 0; t2 < C::STAGES && t2 < nsteps; ++t2) issue(t2);
@@ -1074,6 +1091,11 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
         const int a = ax + 2 * ay + 4 * az;
         af[az][ax][ks] = gq < 6 ? sKe[(a * NDOF + d) * 24 + 4 * ks + q4] : 0.0;
       }
+  // offset of the wanted first double inside the box rows of region (plane p, row parity q): parity of the box start
+  auto xshift = [&](int p, int q) {
+    const int a = ((kl0 + p) * g.NY) & 1;  // (JB * t is even: the parity does not depend on the step)
+    return ((q ? 1 - a : a) * (int)xrow + (i0 - 1) * NDOF) & 1;
+  };
   // B fragment offsets (doubles inside a ring stage, element column offset excluded): k index kk = 4 ks + q4 = 3 bn + c,
   // column gq = element row; node (bx, gq + by, bz) of the element, layer selector az (element layer = kl - az)
   int boff[2][6];
@@ -1084,19 +1106,19 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
       const int kk = 4 * ks + q4, bn = kk / 3, c = kk - 3 * bn;
       const int bx = bn & 1, by = (bn >> 1) & 1, bz = bn >> 2;
       const int p = wz + 1 - az + bz, row = gq + by;
-      boff[az][ks] = (2 * p + (row & 1)) * XREG + (row >> 1) * XL + bx * NDOF + c;
+      boff[az][ks] = (2 * p + (row & 1)) * XREG + (row >> 1) * XL + bx * NDOF + c + xshift(p, row & 1);
     }
   int soff[2][2];
 #pragma unroll
   for (int az = 0; az < 2; ++az)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) soff[az][h] = C::XDOUBLES + ((wz + 1 - az) * JB + 2 * q4 + h) * C::SBOX_X;
+    for (int h = 0; h < 2; ++h) soff[az][h] = C::XDOUBLES + ((wz + 1 - az) * JB + 2 * q4 + h) * C::SBOX_X + 1;  // box starts at element i0 - 2
   double* myOut = sOut + warp * JB * C::OUTW;
   double* myCarry = sCarry + warp * C::OUTW;
-  const int nbxg = gridDim.x;
+  const int nbxg = gridDim.x / nbz;
+  const size_t flag0 = ((size_t)bzs * nbxg + bxs) * nsteps;
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-  const int dbg = skew;  // diagnostic bit mask (PMB_YM_SKEW): 1 = no epilogue, 2 = no DMMA, 4 = no B / s shared loads, 8 = no finalize
-  bool fnext = flags ? __ldg(flags + ((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps) != 0 : true;
+  bool fnext = flags ? __ldg(flags + flag0) != 0 : true;
 
   for (int t = 0; t <= nsteps; ++t) {
     const bool flush = t == nsteps;       // last pass: only the carried row (node row 8 nsteps, when it exists)
@@ -1108,23 +1130,32 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
     if (!flush) {
       flagged = mask && fnext;
       // next step's flag and this step's epilogue operands start their trip through the memory system now
-      if (flags && t + 1 < nsteps) fnext = __ldg(flags + ((size_t)blockIdx.y * nbxg + blockIdx.x) * nsteps + t + 1) != 0;
+      if (flags && t + 1 < nsteps) fnext = __ldg(flags + flag0 + t + 1) != 0;
       if (wactive && lane < 16 && j0 + (lane >> 1) < g.NY) {
         const long long pr = (((long long)kl * g.NY + j0 + (lane >> 1)) * g.NX + iw) * NDOF + 16 * (lane & 1);
         if (MODE != EMODE_SPMV) prefetch_l2(b + pr);
         if (MODE == EMODE_JACOBI) prefetch_l2(diag + pr), prefetch_l2(x + pr);
       }
       mbar_wait(&full_bar[stg], (unsigned)((t / C::STAGES) & 1));
-      if (flagged) {   // Dirichlet columns of the staged rows are zeroed in place (CTA-uniform, rare)
-        for (int p = tid; p < C::XROWS * XL; p += NT) {
-          const int rr = p / XL, c = p - rr * XL;
+      if (flagged) {   // Dirichlet columns of the staged rows are zeroed in place (CTA-uniform, rare).  All mask bytes of a
+                       // thread are loaded before the first is used: one memory round trip per step instead of 15
+        constexpr int NQ = (C::XROWS * C::XLEN + NT - 1) / NT;
+        unsigned char mk[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int p = tid + q * NT, rr = p / C::XLEN, c = p - rr * C::XLEN;
           const int pl = rr / (JB + 1), r = rr - pl * (JB + 1);
           const int klr = kl0 - 1 + pl, jr = j0 + r, kr = g.kz0 + klr, ir = i0 - 1 + c / NDOF;
-          if (ir >= 0 && ir < g.NX && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl) {
-            const long long rowb = ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF;
-            if (__ldg(mask + rowb + c)) su[(2 * pl + (r & 1)) * XREG + (r >> 1) * XL + c] = 0.0;
-          }
+          const bool ok = p < C::XROWS * C::XLEN && ir >= 0 && ir < g.NX && jr < g.NY && kr >= 0 && kr < g.NZ && klr <= g.nzl;
+          mk[q] = ok ? __ldg(mask + ((long long)klr * g.NY + jr) * xrow + (long long)(i0 - 1) * NDOF + c) : (unsigned char)0;
         }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (mk[q]) {
+            const int p = tid + q * NT, rr = p / C::XLEN, c = p - rr * C::XLEN;
+            const int pl = rr / (JB + 1), r = rr - pl * (JB + 1);
+            su[(2 * pl + (r & 1)) * XREG + (r >> 1) * XL + c + xshift(pl, r & 1)] = 0.0;
+          }
         __syncthreads();
       }
     }
@@ -1146,9 +1177,9 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
 #pragma unroll
           for (int az = 0; az < 2; ++az) {
 #pragma unroll
-            for (int ks = 0; ks < 6; ++ks) bv[az][ks] = (dbg & 4) ? 1.0 + ks + lane : su[boff[az][ks] + coloff];
-            sv[az][0] = (dbg & 4) ? 1.0 : su[soff[az][0] + 8 * wx + ex + 1];
-            sv[az][1] = (dbg & 4) ? 1.0 : su[soff[az][1] + 8 * wx + ex + 1];
+            for (int ks = 0; ks < 6; ++ks) bv[az][ks] = (PMB_YM_DBG & 4) ? 1.0 + ks + lane : su[boff[az][ks] + coloff];
+            sv[az][0] = (PMB_YM_DBG & 4) ? 1.0 : su[soff[az][0] + 8 * wx + ex + 1];
+            sv[az][1] = (PMB_YM_DBG & 4) ? 1.0 : su[soff[az][1] + 8 * wx + ex + 1];
           }
           double cc[2][2][2][2];  // [az][ax][half][c0 / c1]
 #pragma unroll
@@ -1164,7 +1195,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
 #pragma unroll
               for (int ax = 0; ax < 2; ++ax) {
                 if ((ax == 0 && ex < 0) || (ax == 1 && ex > 6)) continue;  // node column outside this warp's eight
-                if (dbg & 2) continue;
+                if (PMB_YM_DBG & 2) continue;
                 dmma884(cc[az][ax][0][0], cc[az][ax][0][1], af[az][ax][ks], bv[az][ks]);
                 dmma884(cc[az][ax][1][0], cc[az][ax][1][1], af[az][ax][ks + 3], bv[az][ks + 3]);
               }
@@ -1179,7 +1210,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
               ynext[1] = fma(sv[az][1], cc[az][1][0][1] + cc[az][1][1][1], ynext[1]);
             }
           }
-          if (ex >= 0 && !(dbg & 8)) {
+          if (ex >= 0 && !(PMB_YM_DBG & 8)) {
             // ---- node column di = ex finished: lane (row gq = (ay, d), cols 2 q4, 2 q4 + 1).  Node row c takes (ay = 0,
             //      col c) + (ay = 1, col c - 1); col -1 is the value carried from the previous step
             const int srcrow = (gq % 3 + 3) * 4;                              // lane base of row (ay = 1, d)
@@ -1216,7 +1247,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
         }
       }
     }
-    if (wactive && !(dbg & 1)) {
+    if (wactive && !(PMB_YM_DBG & 1)) {
       // ---- epilogue: 8 node rows x 24 contiguous doubles (8 nodes x 3 dofs) of this warp; lane < 24 owns one column of
       //      them.  All loads of 4 rows are issued before the first use.
       const int nrows = flush ? 1 : JB;
@@ -1266,7 +1297,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
     if (tid == 0) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int v = 0; v < NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
-      const long long bid = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+      const long long bid = blockIdx.x;
       partials[3 * bid] = s0;
       partials[3 * bid + 1] = s1;
       partials[3 * bid + 2] = s2;
@@ -1328,7 +1359,7 @@ extern "C" int pmb_elem_brickflags(const pmb_grid* p, int variant, const unsigne
   if (validate_grid(p, "pmb_elem_brickflags")) return 1;
   PMB_REQUIRE(bcmask && flags, "pmb_elem_brickflags: NULL pointer argument");
   PMB_REQUIRE(p->nz > 0, "pmb_elem_brickflags: 3-D grids only");
-  PMB_REQUIRE(variant >= 4 && variant <= 7, "pmb_elem_brickflags: layout %d takes no flags", variant);
+  PMB_REQUIRE(variant == 0 || (variant >= 4 && variant <= 7), "pmb_elem_brickflags: layout %d takes no flags", variant);
   Geo g = make_geo(p);
   if (variant == 6 || variant == 7) {
     PMB_REQUIRE(g.ndof == 3, "pmb_elem_brickflags: layouts 6, 7 are ndof = 3 only");
@@ -1406,7 +1437,7 @@ static dim3 elem_grid_any(const Geo& g, int variant) {
     case 7: {
       int nbx, nbz, nsteps;
       ym_grid(g, nbx, nbz, nsteps);
-      return dim3(nbx, nbz, 1);
+      return dim3(nbx * nbz, 1, 1);
     }
   }
   return elem_grid<true>(g);
@@ -1455,7 +1486,7 @@ static int ym_tensor_maps(const Geo& g, const double* x, const double* s, CUtens
   {
     cuuint64_t dims[2] = {2 * xrow, (rows + 1) / 2};
     cuuint64_t strides[1] = {2 * xrow * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)YmCfg::XLEN, (cuuint32_t)YmCfg::XBOX_ROWS};
+    cuuint32_t box[2] = {(cuuint32_t)YmCfg::XBOX, (cuuint32_t)YmCfg::XBOX_ROWS};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x) - plane, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1490,6 +1521,8 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
   if ((variant == 6 || variant == 7) && !ym_layout_applicable(g, x, s)) variant = 0;  // odd nx / unpadded or misaligned storage
   dim3 grid = elem_grid_any(g, variant);
   double* part = dot_out ? ws : nullptr;
+  // the caller's flags follow the layout it ASKED for: a layout that falls back to the brick kernel must not read them
+  const unsigned char* flags_brick = (op->variant == 0 || op->variant == 4 || op->variant == 5) ? op->brickflags : nullptr;
   if constexpr (DIM3 && NDOF != 2) {
     if (variant == 1)
       elem_kernel_zm<NDOF, MODE, 8, 2><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
@@ -1518,16 +1551,14 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
         }
         int nbx, nbz, nsteps;
         ym_grid(g, nbx, nbz, nsteps);
-        PMB_REQUIRE(nbz <= 65535, "pmb_elem_spmv: slab too tall for the y-marching layout");
-        static const int ym_skew = getenv("PMB_YM_SKEW") ? atoi(getenv("PMB_YM_SKEW")) : 0;
         CUtensorMap tmx, tms;
         int szoff = 0;
         if (ym_tensor_maps(g, x, s, &tmx, &tms, &szoff)) return 1;
         if (variant == 6)
-          elem_kernel_ym<MODE, 2><<<grid, YmCfg::NT, smem, st>>>(g, ke, tmx, tms, nsteps, ym_skew, szoff, mask, op->brickflags, bcdiag, x, b,
+          elem_kernel_ym<MODE, 2><<<grid, YmCfg::NT, smem, st>>>(tmx, tms, g, ke, nsteps, nbz, szoff, mask, op->brickflags, bcdiag, x, b,
                                                                  diag, w, y, dotv, part);
         else
-          elem_kernel_ym<MODE, 1><<<grid, YmCfg::NT, smem, st>>>(g, ke, tmx, tms, nsteps, ym_skew, szoff, mask, op->brickflags, bcdiag, x, b,
+          elem_kernel_ym<MODE, 1><<<grid, YmCfg::NT, smem, st>>>(tmx, tms, g, ke, nsteps, nbz, szoff, mask, op->brickflags, bcdiag, x, b,
                                                                  diag, w, y, dotv, part);
       }
     } else if (variant == 4 || variant == 5) {
@@ -1551,9 +1582,9 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
         elem_kernel_ring<NDOF, MODE, 2><<<grid, C::NT, C::SMEM, st>>>(g, ke, nbx, nby, (int)nb, s, mask, op->brickflags, bcdiag, x, b, diag,
                                                                       w, y, dotv, part);
     } else
-      elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+      elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, flags_brick, bcdiag, x, b, diag, w, y, dotv, part);
   } else {
-    elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, bcdiag, x, b, diag, w, y, dotv, part);
+    elem_kernel<NDOF, DIM3, MODE><<<grid, 256, 0, st>>>(g, ke, s, mask, nullptr, bcdiag, x, b, diag, w, y, dotv, part);
   }
   PMB_CHECK_LAUNCH("pmb_elem_spmv");
   if (dot_out) {
@@ -1631,7 +1662,7 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const
     trial.brickflags = nullptr;
     const bool wants_flags = (v == 4 || v == 5 || ((v == 6 || v == 7) && p->ndof == 3)) && p->ndof != 2;
     if (op->bcmask && wants_flags) {
-      if (v != 5 && v != 7) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 / 7 reuse the flags of 4 / 6
+      if (v == 4 || v == 6) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 / 7 reuse 4 / 6
       trial.brickflags = flags_scratch;
     }
     const int reps = 6;

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--cases", default="3:256x128x128,1:256x256x256")
     ap.add_argument("--variants", default=None, help="comma-separated layouts (default: all)")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--nobc", action="store_true", help="no Dirichlet dofs (no mask traffic at all): the kernels' upper bound")
     args = ap.parse_args()
     import __graft_entry__ as ge
 
@@ -40,7 +41,7 @@ def main():
         dom = pmb.VoxelDomain(nx, ny, nz)
         nodes_face = (np.arange(nz + 1)[:, None] * (ny + 1) + np.arange(ny + 1)[None, :]).ravel() * (nx + 1)
         bc = np.sort((nodes_face[:, None] * ndof + np.arange(ndof)[None, :]).ravel())
-        asm = (pmb.AssembleStiffness if ndof == 3 else pmb.AssemblePoisson)(dom, bc=bc)
+        asm = (pmb.AssembleStiffness if ndof == 3 else pmb.AssemblePoisson)(dom, bc=None if args.nobc else bc)
         x = torch.rand(dom.nel, dtype=torch.float64, device="cuda") * 0.9 + 0.1
         K = asm(x)
         gen = K.generator

@@ -133,8 +133,8 @@ def filterconv_slabs(rank, world):
 
 def design_updates(rank, world):
     """Three OC and three MMA design updates with the design vector distributed over the slabs (volume sum, Newton sums,
-    maxima and step lengths all-reduced) against the numpy oracle on the whole grid: designs agree to 1e-6 / 1e-5, responses
-    to 1e-6 relative."""
+    maxima and step lengths all-reduced) against the numpy oracle on the whole grid (OC: first update 1e-6, later ones at the
+    resolution of its bisection; MMA: designs 1e-5, responses 1e-6 relative)."""
     import pymoto_b200 as pmb
     from pymoto_b200 import device as dv
     from oracle import Grid
@@ -196,10 +196,14 @@ def design_updates(rank, world):
     for it, (c_ref, x_ref) in enumerate(oc_hist):
         xl, g, _ = oc.step(xl)
         xg = gathered(xl)
-        assert abs(g - c_ref) <= 1e-6 * abs(c_ref), ("OC objective", it, g, c_ref)
-        assert np.abs(xg - x_ref).max() <= 1e-6, ("OC design", it, np.abs(xg - x_ref).max())
+        # the bisection on the multiplier stops at l2 - l1 <= 1e-4 and branches on the sign of (volume - target): a last-bit
+        # difference in dg can end it one step apart, which moves the design by O(1e-4) -- the first update (identical
+        # inputs) is compared tightly, the following ones at the bisection's own resolution
+        tol_x, tol_c = (1e-6, 1e-6) if it == 0 else (5e-4, 1e-4)
+        assert abs(g - c_ref) <= tol_c * abs(c_ref), ("OC objective", it, g, c_ref)
+        assert np.abs(xg - x_ref).max() <= tol_x, ("OC design", it, np.abs(xg - x_ref).max())
     if rank == 0:
-        print(f"[dist_check] OC on {world} slabs: 3 updates match the oracle (|dx| <= 1e-6), last objective {g!r}")
+        print(f"[dist_check] OC on {world} slabs: 3 updates match the oracle (first 1e-6, then the bisection tolerance), last objective {g!r}")
     pmb.slab.reset()
 
     sx, resp, fn, _ = network(True)
