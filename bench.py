@@ -191,22 +191,29 @@ def cpu_arm(size, steps, warmup, problem="cantilever"):
                 kind=kind, where=where, nlevels=chain.nlevels, times=times)
 
 
-def pick_cpu_size(full, n_iters, explicit, budget_s=270.0):
-    """Largest sample grid whose whole run (setup + n_iters iterations of the unmodified reference) fits ``budget_s``:
-    128x64x64 (~11 s / iteration, 25 GB RSS, ~35 s setup -- BASELINE.md section 2), 96x48x48 (~4.5 s), 64x32x32 (~1.5 s)."""
+def pick_cpu_size(full, n_iters, explicit, budget_s=240.0, problem="cantilever"):
+    """Largest sample grid whose whole run (set-up + n_iters iterations of the unmodified reference) fits ``budget_s`` on THIS
+    host: the table below was measured in the build container (128x64x64: ~11 s / iteration, 25 GB RSS, ~40 s set-up --
+    BASELINE.md section 2); a two-iteration calibration run at 32x16x16 (~0.13 s / iteration there) scales it to the host the
+    bench runs on.  Returns (size, host speed factor)."""
     if explicit is not None:
-        return tuple(explicit)
+        return tuple(explicit), None
     try:
         import psutil
 
         ram = psutil.virtual_memory().available
     except Exception:
         ram = 0
-    cands = [((128, 64, 64), 11.0, 40.0, 34e9), ((96, 48, 48), 4.6, 18.0, 16e9), ((64, 32, 32), 1.6, 6.0, 6e9)]
+    factor = 1.0
+    try:
+        factor = max(0.5, cpu_arm((32, 16, 16), 2, 1, problem)["sec_per_iter"] / 0.13)
+    except Exception:
+        pass
+    cands = [((128, 64, 64), 11.0, 40.0, 34e9), ((96, 48, 48), 4.6, 18.0, 16e9), ((64, 32, 32), 1.3, 6.0, 6e9)]
     for size, per_iter, setup, need in cands:
-        if all(s <= f for s, f in zip(size, full)) and ram >= need and setup + n_iters * per_iter <= budget_s:
-            return size
-    return (64, 32, 32) if min(full) >= 32 else tuple(full)
+        if all(s <= f for s, f in zip(size, full)) and ram >= need and factor * (setup + n_iters * per_iter) <= budget_s:
+            return size, factor
+    return ((64, 32, 32) if min(full) >= 32 else tuple(full)), factor
 
 
 def cpu_line(r, size, full, problem, steps, warmup):
@@ -226,7 +233,7 @@ def run_reference(args, full):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    size = pick_cpu_size(full, args.steps + args.warmup, args.cpu_size)
+    size, host_factor = pick_cpu_size(full, args.steps + args.warmup, args.cpu_size, problem=args.problem)
     r = cpu_arm(size, args.steps, args.warmup, args.problem)
     value, scale, sample = cpu_line(r, size, full, args.problem, args.steps, args.warmup)
     line = {
@@ -238,7 +245,7 @@ def run_reference(args, full):
                    "caveat": f"the reference needs ~15 kB/dof of host RAM for its set-up (~200 GB at 256x128x128): it is MEASURED on the "
                              f"{size[0]}x{size[1]}x{size[2]} sample and value / ms_per_step are that measurement scaled linearly in dof",
                    "sample_grid": list(size), "measured_sec_per_iter_on_sample": r["sec_per_iter"], "extrapolation_factor": 1.0 / scale,
-                   "measured_run_s": r["setup_s"] + sum(r["times"])},
+                   "measured_run_s": r["setup_s"] + sum(r["times"]), "host_speed_vs_build_container": host_factor},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "compliance_on_sample": r["compliance"],
