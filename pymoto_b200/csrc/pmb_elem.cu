@@ -13,6 +13,7 @@
 // Ke operand straight from c[0x0][...] (compile-time indices after full unrolling).
 #include <cuda.h>
 #include <cstdlib>
+#include <type_traits>
 #include "pmb_tilestream.cuh"
 
 enum { EMODE_SPMV = PMB_SPMV, EMODE_RESID = PMB_RESIDUAL, EMODE_JACOBI = PMB_JACOBI };
@@ -1321,6 +1322,8 @@ __global__ void __launch_bounds__(256) elem_ymflags_kernel(Geo g, int nsteps, co
   if (threadIdx.x == 0) flags[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = any ? 1 : 0;
 }
 
+#include "pmb_elem_par.cuh"
+
 static int sm_count_elem() {
   static int n = 0;
   if (n == 0) {
@@ -1350,6 +1353,10 @@ extern "C" long long pmb_elem_brickflags_bytes(const pmb_grid* p, int variant) {
     ym_grid(g, nbx, nbz, nsteps);
     return (long long)nbx * nbz * nsteps;
   }
+  if (variant >= 8 && variant < 8 + PAR_NCFG) {
+    const int ey = PAR_CFG[variant - 8].ey;
+    return (long long)((g.NX + PAR_EX - 2) / (PAR_EX - 1)) * ((g.NY + ey - 2) / (ey - 1)) * (g.nzl + 2);
+  }
   int nbx, nby, nbz;
   ring_bricks(g, nbx, nby, nbz);
   return (long long)nbx * nby * nbz;
@@ -1359,8 +1366,17 @@ extern "C" int pmb_elem_brickflags(const pmb_grid* p, int variant, const unsigne
   if (validate_grid(p, "pmb_elem_brickflags")) return 1;
   PMB_REQUIRE(bcmask && flags, "pmb_elem_brickflags: NULL pointer argument");
   PMB_REQUIRE(p->nz > 0, "pmb_elem_brickflags: 3-D grids only");
-  PMB_REQUIRE(variant == 0 || (variant >= 4 && variant <= 7), "pmb_elem_brickflags: layout %d takes no flags", variant);
+  PMB_REQUIRE(variant == 0 || (variant >= 4 && variant < 8 + PAR_NCFG), "pmb_elem_brickflags: layout %d takes no flags", variant);
   Geo g = make_geo(p);
+  if (variant >= 8) {
+    PMB_REQUIRE(g.ndof != 2, "pmb_elem_brickflags: the parity-block layouts are ndof = 1, 3 only");
+    const int ey = PAR_CFG[variant - 8].ey;
+    const int nbx = (g.NX + PAR_EX - 2) / (PAR_EX - 1), nby = (g.NY + ey - 2) / (ey - 1);
+    PMB_REQUIRE(nby <= 65535 && g.nzl + 2 <= 65535, "pmb_elem_brickflags: grid too large");
+    elem_parflags_kernel<<<dim3(nbx, nby, g.nzl + 2), 128, 0, (cudaStream_t)stream>>>(g, ey, bcmask, flags);
+    PMB_CHECK_LAUNCH("pmb_elem_brickflags");
+    return 0;
+  }
   if (variant == 6 || variant == 7) {
     PMB_REQUIRE(g.ndof == 3, "pmb_elem_brickflags: layouts 6, 7 are ndof = 3 only");
     int nbx, nbz, nsteps;
@@ -1407,7 +1423,9 @@ static dim3 elem_grid(const Geo& g) {
 //      staged bricks (elem_kernel_ring) at 3 / 2 CTAs per SM, 6 = y-marching FP64 tensor-core layout with in-register
 //      accumulation (elem_kernel_ym, ndof 3 only).  The layout is a field of the caller's pmb_elem_op: no process-wide state.
 //      Layouts 0, 1, 2, 4, 5 produce bit-identical y; 3 and 6 (tensor-core accumulation order) agree to rounding.
-enum { PMB_ELEM_VARIANTS = 8 };
+//      8 / 9 = parity-block layout (elem_kernel_par, ndof 1 or 3; needs an element matrix with the reflection symmetry of
+//      a cuboid voxel, otherwise layout 0 runs): 32 x 8 / 32 x 4 element columns per CTA; agrees with layout 0 to rounding.
+enum { PMB_ELEM_VARIANTS = 8 + PAR_NCFG };
 extern "C" int pmb_elem_num_variants(void) { return PMB_ELEM_VARIANTS; }
 
 static int effective_variant(const Geo& g, int variant) {
@@ -1439,6 +1457,11 @@ static dim3 elem_grid_any(const Geo& g, int variant) {
       ym_grid(g, nbx, nbz, nsteps);
       return dim3(nbx * nbz, 1, 1);
     }
+  }
+  if (variant >= 8 && variant < 8 + PAR_NCFG) {
+    const ParLaunchCfg c = PAR_CFG[variant - 8];
+    const int zl = par_zl(g, c.ey, c.minb, sm_count_elem());
+    return dim3((g.NX + PAR_EX - 2) / (PAR_EX - 1), (g.NY + c.ey - 2) / (c.ey - 1), (g.nzl + zl - 1) / zl);
   }
   return elem_grid<true>(g);
 }
@@ -1519,6 +1542,12 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
   const double bcdiag = op->bcdiagval;
   int variant = effective_variant(g, op->variant);
   if ((variant == 6 || variant == 7) && !ym_layout_applicable(g, x, s)) variant = 0;  // odd nx / unpadded or misaligned storage
+  [[maybe_unused]] ParBlocks<NDOF> kb;
+  if (variant >= 8) {
+    bool ok = false;
+    if constexpr (DIM3 && NDOF != 2) ok = par_blocks<NDOF>(op->Ke_host, kb);
+    if (!ok) variant = 0;  // element matrix without the reflection symmetry of a cuboid voxel
+  }
   dim3 grid = elem_grid_any(g, variant);
   double* part = dot_out ? ws : nullptr;
   // the caller's flags follow the layout it ASKED for: a layout that falls back to the brick kernel must not read them
@@ -1561,6 +1590,34 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
           elem_kernel_ym<MODE, 1><<<grid, YmCfg::NT, smem, st>>>(tmx, tms, g, ke, nsteps, nbz, szoff, mask, op->brickflags, bcdiag, x, b,
                                                                  diag, w, y, dotv, part);
       }
+    } else if (variant >= 8) {
+      const unsigned char* pflags = op->variant == variant ? op->brickflags : nullptr;   // flags follow the layout asked for
+      int rc = 1;
+      auto launch = [&](auto tag) {
+        constexpr int I = decltype(tag)::value;
+        constexpr ParLaunchCfg c = PAR_CFG[I];
+        auto kern = elem_kernel_par<NDOF, MODE, c.ey, c.minb, c.csm>;
+        constexpr size_t smem = par_smem_bytes<NDOF, c.ey, c.csm>();
+        static bool configured = false;
+        if (!configured) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) {
+            rc = pmb_set_error("elem_kernel_par attribute: %s", cudaGetErrorString(e));
+            return;
+          }
+          configured = true;
+        }
+        kern<<<grid, PAR_EX * c.ey, smem, st>>>(g, kb, par_zl(g, c.ey, c.minb, sm_count_elem()), 0, s, mask, pflags, bcdiag, x, b, diag, w,
+                                                y, dotv, part);
+        rc = 0;
+      };
+      switch (variant - 8) {
+        case 0: launch(std::integral_constant<int, 0>{}); break;
+        case 1: launch(std::integral_constant<int, 1>{}); break;
+        case 2: launch(std::integral_constant<int, 2>{}); break;
+        case 3: launch(std::integral_constant<int, 3>{}); break;
+      }
+      if (rc) return rc;
     } else if (variant == 4 || variant == 5) {
       using C = RingCfg<NDOF>;
       static bool configured = false;
@@ -1640,8 +1697,14 @@ extern "C" int pmb_elem_spmv(const pmb_grid* p, int mode, const pmb_elem_op* op,
 // flags_scratch: pmb_elem_autotune_flag_bytes(g) bytes (the brick flags are layout-specific and recomputed per layout;
 // may be NULL when op->bcmask is NULL).  The caller stores *best in its pmb_elem_op.  Not capturable into a CUDA graph.
 extern "C" long long pmb_elem_autotune_flag_bytes(const pmb_grid* p) {
-  const long long a = pmb_elem_brickflags_bytes(p, 4), b = p->ndof == 3 ? pmb_elem_brickflags_bytes(p, 6) : 0;
-  return a > b ? a : b;
+  long long m = pmb_elem_brickflags_bytes(p, 4);
+  const long long b = p->ndof == 3 ? pmb_elem_brickflags_bytes(p, 6) : 0;
+  m = b > m ? b : m;
+  for (int v = 8; v < PMB_ELEM_VARIANTS; ++v) {
+    const long long c = pmb_elem_brickflags_bytes(p, v);
+    m = c > m ? c : m;
+  }
+  return m;
 }
 
 extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const double* x, const double* b, const double* diag,
@@ -1660,9 +1723,9 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const
   for (int v = 0; v < PMB_ELEM_VARIANTS && !rc; ++v) {
     trial.variant = v;
     trial.brickflags = nullptr;
-    const bool wants_flags = (v == 4 || v == 5 || ((v == 6 || v == 7) && p->ndof == 3)) && p->ndof != 2;
+    const bool wants_flags = (v == 4 || v == 5 || ((v == 6 || v == 7) && p->ndof == 3) || v >= 8) && p->ndof != 2;
     if (op->bcmask && wants_flags) {
-      if (v == 4 || v == 6) rc = pmb_elem_brickflags(p, v == 6 ? 6 : 4, op->bcmask, flags_scratch, stream);  // 5 / 7 reuse 4 / 6
+      if (v == 4 || v == 6 || v >= 8) rc = pmb_elem_brickflags(p, v, op->bcmask, flags_scratch, stream);  // 5 / 7 reuse 4 / 6
       trial.brickflags = flags_scratch;
     }
     const int reps = 6;
@@ -1676,7 +1739,7 @@ extern "C" int pmb_elem_autotune(const pmb_grid* p, const pmb_elem_op* op, const
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= reps;
     if (ms_out) ms_out[v] = ms;
-    const bool rounding = (v == 3 || v == 6 || v == 7) && p->ndof == 3;
+    const bool rounding = ((v == 3 || v == 6 || v == 7) && p->ndof == 3) || v >= 8;
     if (!rc && ms < best_ms && (allow_rounding || !rounding)) best_ms = ms, best = v;
   }
   cudaEventDestroy(e0);

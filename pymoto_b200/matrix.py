@@ -57,6 +57,8 @@ class ElemGenerator:
             mask_ptr = None if self.mask is None else self.mask.data_ptr() + k_rel * plane
             flags = None
             fv = 6 if (self.variant in (6, 7) and g.ndof == 3) else (4 if self.variant in (4, 5) else None)
+            if self.variant >= 8:
+                fv = self.variant
             if mask_ptr is not None and g.nz > 0 and g.ndof != 2 and fv is not None:
                 flags = self._flags.get(key[:2] + (fv,))
                 if flags is None:

@@ -620,6 +620,74 @@ def test_matrix_free_kernel_variants_bit_identical(pmb, shape, ndof):
         gen.variant = saved
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ndof,units", [((37, 9, 7), 3, (1.0, 1.0, 1.0)), ((33, 6, 4), 3, (1.0, 0.5, 2.0)), ((40, 7, 6), 1, (1.0, 1.0, 1.0)),
+                                              ((64, 32, 32), 3, (1.0, 1.0, 1.0)), ((5, 20, 19), 3, (0.25, 1.0, 1.5)), ((66, 16, 5), 1, (2.0, 0.5, 1.0)),
+                                              ((31, 8, 4), 3, (1.0, 1.0, 1.0)), ((30, 7, 33), 3, (1.0, 1.0, 1.0)), ((62, 14, 3), 3, (1.0, 1.0, 1.0))])
+def test_matrix_free_parity_block_layout(pmb, shape, ndof, units):
+    """Layouts 8 / 9 (parity-block form of the element product, pmb_elem_par.cuh) on the reference's own hex8 stiffness /
+    conductivity matrices (cubic and cuboid voxels): every mode, the fused dot products and a sub-slab agree with layout 0 to
+    1e-12 of the field magnitude; an element matrix WITHOUT the reflection symmetry silently runs layout 0 (bit-identical)."""
+    import ctypes as C
+
+    from pymoto_b200 import _lib, device as dv
+    from pymoto_b200.matrix import make_grid
+
+    rng = np.random.default_rng(11)
+    gr = Grid(*shape)
+    dom = pmb.VoxelDomain(*shape, unitx=units[0], unity=units[1], unitz=units[2])
+    bc = np.unique(rng.integers(0, gr.nnodes * ndof, 23))
+    asm = (pmb.AssembleStiffness if ndof == 3 else pmb.AssemblePoisson)(dom, bc=bc)
+    K = asm(rng.random(gr.nel) * 0.9 + 0.1)
+    n = K.shape[0]
+    vd, bd = dv.to_device(rng.standard_normal(n)), dv.to_device(rng.standard_normal(n))
+    D = K.diagonal_device()
+    gen = K.generator
+    saved = gen.variant
+    try:
+        ref = {}
+        for variant in (0, 8, 9, 10, 11):
+            gen.variant = variant
+            for mode in (_lib.SPMV, _lib.RESIDUAL, _lib.JACOBI):
+                out, d3 = dv.zeros(n), dv.empty(3)
+                K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
+                got = (out.cpu().numpy(), d3.cpu().numpy())
+                if variant == 0:
+                    ref[mode] = got
+                else:
+                    scale = max(1.0, np.abs(ref[mode][0]).max())
+                    np.testing.assert_allclose(got[0], ref[mode][0], rtol=0, atol=1e-12 * scale, err_msg=f"variant {variant} mode {mode}")
+                    assert np.abs(got[0] - ref[mode][0]).max() > 0.0 or n < 100, "layout 0 ran instead of the parity-block layout"
+                    np.testing.assert_allclose(got[1], ref[mode][1], rtol=1e-10, atol=1e-8)
+            if variant == 0 or K.grid.nz < 5:
+                continue
+            g, k0, npl = K.grid, 1, 3
+            sg = make_grid(g.nx, g.ny, g.nz, g.ndof, k0, npl)
+            plane = K.plane
+            out = dv.zeros(n)
+            xin = K._padded(vd)
+            _lib.call("pmb_elem_spmv", sg, _lib.JACOBI, C.byref(gen.op(sg, k0)), xin.data_ptr() + 8 * k0 * plane,
+                      bd.data_ptr() + 8 * k0 * plane, D.data_ptr() + 8 * k0 * plane, 0.5, out.data_ptr() + 8 * k0 * plane,
+                      None, None, None, dv.stream())
+            want = np.zeros(n)
+            want[k0 * plane:(k0 + npl) * plane] = ref[_lib.JACOBI][0][k0 * plane:(k0 + npl) * plane]
+            np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()))
+        # no reflection symmetry (x displacement coupled to a y difference with one sign only): layout 0 runs
+        Ke = np.array(asm._Ke_host, copy=True).reshape(8 * ndof, 8 * ndof)
+        Ke[0, -1] += 0.05
+        Ke[-1, 0] += 0.05
+        K2 = pmb.AssembleGeneral(dom, Ke, bc=bc)(rng.random(gr.nel))
+        outs = []
+        for variant in (0, 8):
+            K2.generator.variant = variant
+            out = dv.zeros(n)
+            K2.apply(_lib.SPMV, vd, out)
+            outs.append(out.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])
+    finally:
+        gen.variant = saved
+
+
 # ------------------------------------------------------------------------------------------------ FilterConv (next row f1)
 FILTERCONV_KW = {
     "sym3d": dict(radius=2.0),
