@@ -670,15 +670,23 @@ def run_b200(args, full):
         pass
     if was_mf and not args.csr:
         mf_ms = time_sweeps(A, *bufs0, D)
-        flops = 2.0 * 8 * (8 * ndof_ * ndof_ + ndof_) * (n / ndof_)  # 8 elements x (8 nodes x ndof^2 + ndof) FMA per node
+        gen = A.generator
+        dense_flops = 2.0 * 8 * (8 * ndof_ * ndof_ + ndof_) * (n / ndof_)  # 8 elements x (8 nodes x ndof^2 + ndof) FMA per node
+        if gen.variant >= 8 and ndof_ in (1, 3):
+            # parity-block layouts (pmb_elem_par.cuh): per element 8 blocks of ndof x ndof (2 flop per entry) + density scaling
+            # (8 ndof) + butterflies: forward 16 ndof (x / y of one plane 8 ndof, z 8 ndof), transposed 20 ndof (z 8 ndof, carry
+            # 4 ndof, y / x 8 ndof) + 3 ndof to gather the node + ~4 ndof epilogue; one element per node
+            flops = (2.0 * 8 * ndof_ * ndof_ + (8 + 16 + 20 + 3 + 4) * ndof_) * (n / ndof_)
+        else:
+            flops = dense_flops
         mf_bytes = 40 * n + 8 * nel
         tf = flops / (mf_ms * 1e-3) / 1e12
         hbm_view = {"algorithmic_bytes": mf_bytes, "achieved": mf_bytes / (mf_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": mf_bytes / (mf_ms * 1e-3) / 1e9 / hbm_peak}
-        gen = A.generator
         common = {"kernel": f"matrix-free finest-level operator, layout {gen.variant} of pmb_elem_spmv (Jacobi sweep from the element densities)",
                   "kernel_ms": mf_ms, "launches_per_step": fine_mf / K, "share_of_step": (fine_mf / K) * mf_ms / step_avg_ms,
-                  "flops_per_launch": flops, "fp64_probe_tflops": fp64, "layout_ms_autotune": DeviceCSR.elem_timings_ms.get(ndof_),
+                  "flops_per_launch": flops, "dense_product_flops_per_launch": dense_flops,
+                  "dense_equivalent_tflops": dense_flops / (mf_ms * 1e-3) / 1e12, "fp64_probe_tflops": fp64, "layout_ms_autotune": DeviceCSR.elem_timings_ms.get(ndof_),
                   "traffic": traffic, "traffic_source": traffic_src, "peak_source": "pmb_probe_fp64 in this run (register-only DFMA / DMMA streams)",
                   "hbm_peak_source": peak_src}
         # arithmetic intensity flops / byte vs the ridge fp64_peak / hbm_peak decides which roof bounds the kernel

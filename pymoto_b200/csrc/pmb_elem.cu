@@ -1596,8 +1596,8 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
       auto launch = [&](auto tag) {
         constexpr int I = decltype(tag)::value;
         constexpr ParLaunchCfg c = PAR_CFG[I];
-        auto kern = elem_kernel_par<NDOF, MODE, c.ey, c.minb, c.csm>;
-        constexpr size_t smem = par_smem_bytes<NDOF, c.ey, c.csm>();
+        auto kern = elem_kernel_par<NDOF, MODE, c.ey, c.minb>;
+        constexpr size_t smem = ParCfg<NDOF, c.ey>::SMEM;
         static bool configured = false;
         if (!configured) {
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1607,7 +1607,7 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
           }
           configured = true;
         }
-        kern<<<grid, PAR_EX * c.ey, smem, st>>>(g, kb, par_zl(g, c.ey, c.minb, sm_count_elem()), 0, s, mask, pflags, bcdiag, x, b, diag, w,
+        kern<<<grid, PAR_EX * c.ey, smem, st>>>(g, kb, par_zl(g, c.ey, c.minb, sm_count_elem()), s, mask, pflags, bcdiag, x, b, diag, w,
                                                 y, dotv, part);
         rc = 0;
       };

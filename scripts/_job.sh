@@ -1,6 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "parity_block or variants_bit_identical" 2>&1 | tail -15 > gpurun_out/r2v_tests.log
-tail -3 gpurun_out/r2v_tests.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"elem_kernel_par" -s 3 -c 1 -o gpurun_out/prof_par3_r2b python scripts/time_elem.py --variants 8 --reps 2 --cases 3:256x128x128 > gpurun_out/ncu_par3.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"elem_kernel_par" -s 3 -c 1 -o gpurun_out/prof_par3_r2c python scripts/time_elem.py --variants 10 --reps 2 --cases 3:256x128x128 > gpurun_out/ncu_par3.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"elem_kernel_par" -s 3 -c 1 -o gpurun_out/prof_par1_r2b python scripts/time_elem.py --variants 11 --reps 2 --cases 1:256x256x256 > gpurun_out/ncu_par1.log 2>&1
-ls -la gpurun_out/prof_par*
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -30 > gpurun_out/r2z_tests.log
+tail -4 gpurun_out/r2z_tests.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2z.json 2> gpurun_out/bench_r2z.err; tail -c 300 gpurun_out/bench_r2z.err; head -c 400 gpurun_out/bench_r2z.json
