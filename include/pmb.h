@@ -149,6 +149,17 @@ long long pmb_elem_autotune_flag_bytes(const pmb_grid* g);
 int pmb_elem_autotune(const pmb_grid* g, const pmb_elem_op* op, const double* x, const double* b, const double* diag, double* y,
                       unsigned char* flags_scratch, int allow_rounding, double* ms_out, int* best, void* stream);
 
+/* Symmetric half-stencil storage of a coarse-level operator (whole 3-D grids; replaces the full-stencil sweeps of
+ * pymoto/solvers/iterative.py:236-255 on the levels below the finest): S[slot][d][c][node], slot 0 = diagonal block, slots
+ * 1..13 = the 13 upper neighbours, pmb_sym_doubles(g) doubles = 14/27 of the stencil-CSR values.  pmb_sym_pack copies the
+ * blocks out of stencil-CSR `data` and leaves in stats[0..1] (device, 2 x uint64) the bit patterns of the doubles
+ * max |A_ij - A_ji^T| and max |A_ij|: the caller must not use S when the first is not negligible against the second.
+ * pmb_sym_spmv: modes / epilogues / fused dot products of pmb_spmv (ws: pmb_spmv_ws_doubles). */
+long long pmb_sym_doubles(const pmb_grid* g);
+int pmb_sym_pack(const pmb_grid* g, const double* data, double* S, unsigned long long* stats, void* stream);
+int pmb_sym_spmv(const pmb_grid* g, int mode, const double* S, const double* x, const double* b, const double* diag, double w,
+                 double* y, const double* dotv, double* dot_out, double* ws, void* stream);
+
 /* u = w * (r / diag) */
 int pmb_smooth0(long long n, double w, const double* r, const double* diag, double* u, void* stream);
 

@@ -95,6 +95,9 @@ SIGNATURES = {
     "pmb_elem_brickflags": (_I, [_G, _I, _P, _P, _P]),
     "pmb_elem_autotune_flag_bytes": (_LL, [_G]),
     "pmb_elem_autotune": (_I, [_G, C.POINTER(ElemOp), _P, _P, _P, _P, _P, _I, _P, C.POINTER(C.c_int), _P]),
+    "pmb_sym_doubles": (_LL, [_G]),
+    "pmb_sym_pack": (_I, [_G, _P, _P, _P, _P]),
+    "pmb_sym_spmv": (_I, [_G, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "pmb_ws_doubles": (_LL, []),
     "pmb_smooth0": (_I, [_LL, _D, _P, _P, _P, _P]),
     "pmb_restrict": (_I, [_G, _G, _P, _P, _P]),
@@ -158,7 +161,7 @@ def _kernels_launched(name, args):
     """How many kernels one C-ABI call launches (see the .cu sources)."""
     if name == "pmb_spmv":
         return 2 if args[9] is not None else 1  # + reduce_triples_kernel when the fused dots are requested
-    if name == "pmb_elem_spmv":
+    if name == "pmb_elem_spmv" or name == "pmb_sym_spmv":
         return 2 if args[9] is not None else 1
     if name == "pmb_elem_autotune":
         return 8 * load().pmb_elem_num_variants()  # every variant: 2 warm-up + 6 timed launches
@@ -197,7 +200,7 @@ def _stat_key(name, args):
     """(entry point, detail): detail = (nx, mode) for the operator kernels, (nx, None) for other grid-first calls, (n, None)
     for vector calls -- enough for bench.py to attribute launches and algorithmic bytes to multigrid levels."""
     a0 = args[0] if args else None
-    if name in ("pmb_spmv", "pmb_elem_spmv"):
+    if name in ("pmb_spmv", "pmb_elem_spmv", "pmb_sym_spmv"):
         return (name, (a0.nx, args[1]))
     if isinstance(a0, Grid):
         return (name, (a0.nx, None))

@@ -445,7 +445,7 @@ struct ParLaunchCfg {
   int ey, minb;
 };
 constexpr int PAR_NCFG = 4;
-constexpr ParLaunchCfg PAR_CFG[PAR_NCFG] = {{8, 2}, {16, 1}, {4, 4}, {6, 2}};
+constexpr ParLaunchCfg PAR_CFG[PAR_NCFG] = {{8, 2}, {16, 1}, {12, 1}, {10, 1}};
 
 // planes per CTA: few CTAs lost to the last wave, little redundant layer work (every CTA computes one extra layer)
 static int par_zl(const Geo& g, int ey, int ctas_per_sm, int sms) {

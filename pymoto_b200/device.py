@@ -124,3 +124,9 @@ def lincomb(out, ca, a, cb=None, b=None):
 def scalar_ptr(t, i=0):
     """Device address of element i of a float64 tensor, for _lib.coef(num=..., den=...)."""
     return t.data_ptr() + 8 * i
+
+
+def sm_count():
+    """Streaming multiprocessors of the current device (148 on a B200)."""
+    require_cuda()
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count

@@ -88,6 +88,12 @@ class DeviceCSR:
     # far above that, so the autotune may select them; PMB_ELEM_BITEXACT=1 restricts it to the bit-identical layouts.
     allow_rounding_layouts = os.environ.get("PMB_ELEM_BITEXACT", "0") != "1"
     elem_timings_ms = {}  # filled by the autotune pass: ndof -> [ms per launch of every layout]
+    # Coarse-level operators (level >= 1, whole 3-D grids of at least ``symmetric_min_nodes`` nodes) are ALSO kept in the
+    # symmetric half-stencil layout of pmb_symstore.cu (14 instead of 27 blocks per node) and swept from it; the stencil-CSR
+    # values stay the source of truth (Galerkin products, diagonal, densify).  PMB_SYMMETRIC_STORAGE=0 switches it off.
+    symmetric_storage = os.environ.get("PMB_SYMMETRIC_STORAGE", "0") == "1"
+    symmetric_min_nodes = 100_000
+    symmetric_tol = 1e-10  # max |A_ij - A_ji^T| / max |A_ij| above which the operator is not treated as symmetric
 
     def __init__(self, grid: _lib.Grid, data: torch.Tensor = None, bc_mask: torch.Tensor = None, comm=None, level=0):
         dv.require_cuda()
@@ -112,6 +118,8 @@ class DeviceCSR:
         self._diag_buf = self._nnz_off_buf = None
         self._entry_offsets = {}
         self.generator = None  # ElemGenerator (set by the assembly module) or None
+        self._sym = self._sym_stats = None  # symmetric half-stencil copy of the values (pack_symmetric) + its asymmetry stats
+        self._sym_valid = False
 
     # ---- values
     @property
@@ -121,6 +129,26 @@ class DeviceCSR:
     def invalidate(self):
         """Call after the values changed in place."""
         self._diag = self._nnz_off = None
+        self._sym_valid = False
+
+    def pack_symmetric(self):
+        """(Re)build the symmetric half-stencil copy of the current values if this operator qualifies (coarse level, whole
+        3-D grid, large enough, symmetric to ``symmetric_tol``); the sweeps then read 14 instead of 27 blocks per node.
+        Reads two 8-byte statistics back (one host synchronisation per update)."""
+        g = self.grid
+        self._sym_valid = False
+        if (not DeviceCSR.symmetric_storage or self.level < 1 or self.comm is not None or g.nz == 0 or g.kz0 != 0 or g.nzl != g.nz + 1
+                or self.n // g.ndof < DeviceCSR.symmetric_min_nodes or torch.cuda.is_current_stream_capturing()
+                or ((g.nx + 32) // 32) * ((g.ny + 4) // 4) > 4 * dv.sm_count()):  # one partial triple per CTA (fused dots)
+            return False
+        if self._sym is None:
+            self._sym = dv.empty(_lib.query("pmb_sym_doubles", g))
+            self._sym_stats = dv.empty(2, torch.int64)
+        _lib.call("pmb_sym_pack", g, dv.ptr(self._buf), dv.ptr(self._sym), dv.ptr(self._sym_stats), dv.stream())
+        diff, amax = self._sym_stats.cpu().numpy().view(np.float64)
+        self.asymmetry = float(diff / amax) if amax > 0 else 0.0
+        self._sym_valid = bool(self.asymmetry <= DeviceCSR.symmetric_tol)
+        return self._sym_valid
 
     # ---- vectors this operator can be applied to (halo-padded), halo refresh, global dot products
     def new_vec(self, zero=False):
@@ -217,7 +245,10 @@ class DeviceCSR:
 
     # ---- products
     def _launch(self, gen, grid, mode, data_ptr, k_rel, x_ptr, b_ptr, diag_ptr, w, y_ptr, dotv_ptr, dot_ptr, ws_ptr):
-        if gen is None:
+        if gen is None and self._sym_valid and grid is self.grid and DeviceCSR.symmetric_storage:
+            _lib.call("pmb_sym_spmv", grid, mode, dv.ptr(self._sym), x_ptr, b_ptr, diag_ptr, float(w), y_ptr, dotv_ptr, dot_ptr, ws_ptr,
+                      dv.stream())
+        elif gen is None:
             _lib.call("pmb_spmv", grid, mode, data_ptr, x_ptr, b_ptr, diag_ptr, float(w), y_ptr, dotv_ptr, dot_ptr, ws_ptr,
                       dv.stream())
         else:

@@ -224,6 +224,7 @@ class GeometricMultigrid(Preconditioner):
         if self._replicate:  # first replicated level: every rank gets the whole coarse operator
             A.comm.gather_full(self._Ac_local.data, self.Ac.data, self._coarse_entry_offset)
         self.Ac.invalidate()
+        self.Ac.pack_symmetric()  # levels >= 1 are swept from the symmetric half-stencil copy where it applies
         if self.inner_level is None:
             self.inner_level = SolverDenseInverse()
         self.inner_level.update(self.Ac)
@@ -295,6 +296,7 @@ class GeometricMultigrid(Preconditioner):
                                               gen["bcdiag"], gen["ke"].ctypes.data, gen["ke"].tobytes(), gen.variant)]
             sig += [lvl._buf[k].data_ptr() for k in ("u", "u2", "t", "rc")]
             sig += [lvl.A.grid.kz0, lvl.A.grid.nzl, lvl._replicate]
+            sig += [lvl.A._sym.data_ptr() if (lvl.A._sym_valid and DeviceCSR.symmetric_storage) else None]
             lvl = lvl.inner_level
         if not isinstance(lvl, SolverDenseInverse) or lvl.inv is None:
             return None

@@ -688,6 +688,99 @@ def test_matrix_free_parity_block_layout(pmb, shape, ndof, units):
         gen.variant = saved
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,ndof", [((6, 4, 4), 3), ((8, 8, 8), 1), ((33, 9, 5), 3), ((130, 5, 3), 1), ((20, 18, 3), 2), ((37, 11, 9), 3)])
+def test_symmetric_half_stencil_storage(pmb, shape, ndof):
+    """pmb_sym_pack / pmb_sym_spmv (symmetric half-stencil layout of the coarse-level operators): every mode and the fused dot
+    products against scipy on the assembled CSR and against the stencil-CSR kernel; the measured asymmetry is ~0 for a
+    symmetric operator and the layout is refused (stencil-CSR kernel keeps running) for a non-symmetric one."""
+    from pymoto_b200 import _lib, device as dv
+    from pymoto_b200.matrix import DeviceCSR
+
+    rng = np.random.default_rng(3)
+    gr = Grid(*shape)
+    dom = pmb.VoxelDomain(*shape)
+    Ke = rng.standard_normal((gr.elemnodes * ndof,) * 2)
+    Ke = Ke + Ke.T + 8 * np.eye(Ke.shape[0])
+    bc = np.unique(rng.integers(0, gr.nnodes * ndof, 11))
+    K0 = pmb.AssembleGeneral(dom, Ke, bc=bc)(rng.random(gr.nel))
+    Ks = K0.tocsr()
+    n = K0.shape[0]
+    saved = DeviceCSR.symmetric_min_nodes, DeviceCSR.symmetric_storage
+    DeviceCSR.symmetric_min_nodes, DeviceCSR.symmetric_storage = 0, True
+    try:
+        K = DeviceCSR(K0.grid, data=K0._buf, level=1)  # the same values seen as a coarse-level operator
+        assert K.pack_symmetric() and K.asymmetry <= 1e-15
+        v, b = rng.standard_normal(n), rng.standard_normal(n)
+        vd, bd = dv.to_device(v), dv.to_device(b)
+        scale = np.abs(Ks).dot(np.abs(v)).max()
+        D = K.diagonal_device()
+        calls0 = sum(c for (nm, _), c in _lib.call_stats.items() if nm == "pmb_sym_spmv")
+        for mode, want in ((_lib.SPMV, Ks @ v), (_lib.RESIDUAL, b - Ks @ v), (_lib.JACOBI, v + 0.5 * ((b - Ks @ v) / Ks.diagonal()))):
+            out, d3 = dv.zeros(n), dv.empty(3)
+            K.apply(mode, vd, out, b=bd, diag=D, w=0.5, dotv=bd, dot_out=d3)
+            np.testing.assert_allclose(out.cpu().numpy(), want, rtol=0, atol=1e-13 * scale)
+            np.testing.assert_allclose(d3.cpu().numpy(), [want @ v, v @ b, want @ b], rtol=1e-11, atol=1e-9)
+            out2 = dv.zeros(n)
+            K.apply(mode, vd, out2, b=bd, diag=D, w=0.5)
+            assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
+            ref = dv.zeros(n)
+            was, DeviceCSR.matrix_free = DeviceCSR.matrix_free, False  # level 0 through the stencil-CSR kernel
+            try:
+                K0.apply(mode, vd, ref, b=bd, diag=D, w=0.5)
+            finally:
+                DeviceCSR.matrix_free = was
+            np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=2e-13 * scale)
+        assert sum(c for (nm, _), c in _lib.call_stats.items() if nm == "pmb_sym_spmv") == calls0 + 6
+        # a non-symmetric operator: the layout is refused and the stencil-CSR kernel runs
+        data = K0.data.clone()
+        data[::7] *= 1.5
+        buf = dv.empty(K0.nnz + 2)
+        buf[:K0.nnz], buf[K0.nnz:] = data, 0.0
+        Kn = DeviceCSR(K0.grid, data=buf, level=1)
+        assert not Kn.pack_symmetric() and Kn.asymmetry > 1e-3
+        out = dv.zeros(n)
+        Kn.apply(_lib.SPMV, vd, out)
+        import scipy.sparse as sp
+
+        Kn_s = sp.csr_matrix((data.cpu().numpy(), Ks.indices, Ks.indptr), shape=Ks.shape)
+        np.testing.assert_allclose(out.cpu().numpy(), Kn_s @ v, rtol=0, atol=2e-13 * 1.5 * scale)
+    finally:
+        DeviceCSR.symmetric_min_nodes, DeviceCSR.symmetric_storage = saved
+
+
+@pytest.mark.gpu
+def test_multigrid_solve_with_symmetric_storage_matches(pmb):
+    """The CG + GMG solve with the coarse levels swept from the symmetric half-stencil copy: same iteration count, same
+    solution (1e-9) and compliance (1e-12) as with the stencil-CSR sweeps."""
+    from pymoto_b200 import _lib
+    from pymoto_b200.matrix import DeviceCSR
+
+    nx, ny, nz = 32, 16, 16
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    ndof, bc, f = cantilever(Grid(nx, ny, nz))
+    rng = np.random.default_rng(2)
+    xs = 0.2 + 0.8 * rng.random(dom.nel)
+    saved = DeviceCSR.symmetric_min_nodes, DeviceCSR.symmetric_storage
+    res = {}
+    try:
+        DeviceCSR.symmetric_min_nodes = 0
+        for on in (False, True):
+            DeviceCSR.symmetric_storage = on
+            K = pmb.AssembleStiffness(dom, bc=bc)(xs ** 3)
+            cg = pmb.solvers.CG(preconditioner=pmb.solvers.auto_multigrid(dom)[0], tol=1e-9)
+            n0 = sum(c for (nm, _), c in _lib.call_stats.items() if nm == "pmb_sym_spmv")
+            u = pmb.LinSolve(hermitian=True, solver=cg)(K, f)
+            used = sum(c for (nm, _), c in _lib.call_stats.items() if nm == "pmb_sym_spmv") - n0
+            assert (used > 0) == on
+            res[on] = (np.asarray(u), cg.iterations)
+        np.testing.assert_allclose(res[True][0], res[False][0], rtol=0, atol=1e-9 * np.abs(res[False][0]).max())
+        assert abs(f @ res[True][0] - f @ res[False][0]) <= 1e-12 * abs(f @ res[False][0])
+        assert res[True][1] == res[False][1]
+    finally:
+        DeviceCSR.symmetric_min_nodes, DeviceCSR.symmetric_storage = saved
+
+
 # ------------------------------------------------------------------------------------------------ FilterConv (next row f1)
 FILTERCONV_KW = {
     "sym3d": dict(radius=2.0),
