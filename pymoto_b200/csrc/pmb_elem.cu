@@ -1288,6 +1288,7 @@ __global__ void __launch_bounds__(YmCfg::NT, CTAS)
       }
     }
     if (flush) break;
+    __syncwarp();  // the epilogue's reads of myOut are done before the next step's lanes overwrite it (racecheck: WAR hazard)
   }
   if (partials) {
     d0 = warp_sum(d0);
