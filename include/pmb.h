@@ -332,6 +332,19 @@ int pmb_vcycle(const pmb_mg_desc* mg, const double* r, double* z, void* stream);
 int pmb_pcg_solve(const pmb_mg_desc* mg, const double* b, double* x, double* r, double* q, double* p, double tol, int maxit,
                   int restart, double* scal, double* ws_red, double* ws_spmv, int* iters, double* relres, void* stream);
 
+/* The same solve through a PLAN: descriptor + bound vectors (b: right-hand side, x: start vector in / solution out; r, q, p,
+ * scal, ws_red, ws_spmv as for pmb_pcg_solve) + a CUDA graph of one CG iteration (V-cycle, direction update, product, x / r
+ * update: everything between two host polls), captured on its second occurrence and replayed from then on, also by later
+ * solves through the same plan.  Valid while the addresses in the descriptor, the element matrix behind gen.Ke_host and the
+ * kernel layout stay the same (the operator VALUES may change: they are read from memory).  Iterates are bit-identical to
+ * pmb_pcg_solve.  The plan is the only object the solver side of the library allocates; the caller destroys it. */
+typedef struct pmb_pcg_plan pmb_pcg_plan;
+int pmb_pcg_plan_create(const pmb_mg_desc* mg, const double* b, double* x, double* r, double* q, double* p, double* scal,
+                        double* ws_red, double* ws_spmv, pmb_pcg_plan** plan);
+int pmb_pcg_plan_solve(pmb_pcg_plan* plan, double tol, int maxit, int restart, int* iters, double* relres, void* stream);
+long long pmb_pcg_plan_graph_replays(const pmb_pcg_plan* plan);
+int pmb_pcg_plan_destroy(pmb_pcg_plan* plan);
+
 /* In-run FP64 peak probe for bench.py's roofline (not on the product path): kind 0 = DFMA, 1 = DMMA.8x8x4 register-only
  * streams at 16 warps / SM; *tflops_out (HOST) = best of 3 launches; out: pmb_probe_fp64_out_doubles() device doubles. */
 long long pmb_probe_fp64_out_doubles(void);

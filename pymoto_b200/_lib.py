@@ -146,6 +146,10 @@ SIGNATURES = {
     "pmb_vcycle": (_I, [C.POINTER(MgDesc), _P, _P, _P]),
     "pmb_pcg_solve": (_I, [C.POINTER(MgDesc), _P, _P, _P, _P, _P, _D, _I, _I, _P, _P, _P, C.POINTER(C.c_int),
                            C.POINTER(C.c_double), _P]),
+    "pmb_pcg_plan_create": (_I, [C.POINTER(MgDesc), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_void_p)]),
+    "pmb_pcg_plan_solve": (_I, [_P, _D, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_double), _P]),
+    "pmb_pcg_plan_graph_replays": (_LL, [_P]),
+    "pmb_pcg_plan_destroy": (_I, [_P]),
     "pmb_simp": (_I, [_LL, _D, _I, _P, _P, _P]),
     "pmb_simp_bwd": (_I, [_LL, _D, _I, _P, _P, _P, _P]),
 }
@@ -172,7 +176,7 @@ def _kernels_launched(name, args):
     if name == "pmb_galerkin":
         return 2  # column-collapse + row-collapse passes
     if name == "pmb_dense_invert":
-        return 3 * ((int(args[0]) + 31) // 32)  # pivot block + panels + rank-32 update per 32 pivots
+        return 1  # one cooperative kernel (the three-kernel fallback: 3 per 32 pivots)
     return 1
 
 

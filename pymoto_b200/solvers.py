@@ -429,6 +429,7 @@ class CG(LinearSolver):
         self.restart = restart
         self.verbosity = verbosity
         self.iterations = 0  # products q = A p of the last solve (the reference prints this minus one)
+        self._c_plan, self._c_plan_key, self._c_bufs = None, None, None  # C driver: pmb_pcg_plan + the vectors bound to it
         self.last_residual = None
         super().__init__(A)
 
@@ -452,10 +453,11 @@ class CG(LinearSolver):
             return dv.like_input(torch.stack(cols, dim=1), rhs)
         return dv.like_input(self._solve1(bd.reshape(-1), None if x0 is None else dv.to_device(x0).reshape(-1)), rhs)
 
-    # Drive the whole solve from C (pmb_pcg_solve: same launches in the same order, bit-identical iterates, one host poll
-    # per iteration, no interpreter / ctypes overhead per launch) when the preconditioner is a single-GPU geometric
-    # multigrid hierarchy.  Opt-in: PMB_C_PCG=1 or CG.use_c_driver = True (the Python driver replays the V-cycle as one
-    # CUDA graph instead, which is as fast on large grids).
+    # Drive the whole solve from C (pmb_pcg_plan_solve: same launches in the same order, bit-identical iterates, one host
+    # poll per iteration, every non-restart CG iteration replayed as ONE CUDA graph) when the preconditioner is a single-GPU
+    # geometric multigrid hierarchy.  PMB_C_PCG=1 / CG.use_c_driver = True forces it, PMB_C_PCG=0 forbids it; by default it
+    # is used below ``c_driver_max_rows`` rows, where launch latency sets the pace (the Python driver replays only the
+    # V-cycle as a graph and issues the rest of the iteration through ctypes, which is as fast on large grids).
     use_c_driver = os.environ.get("PMB_C_PCG", "0") == "1"
 
     def _mg_desc(self):
@@ -491,17 +493,30 @@ class CG(LinearSolver):
 
         A, n = self.A, b.numel()
         tstart = time.perf_counter()
-        x = A.new_vec(zero=x0 is None)
-        if x0 is not None:
-            x.copy_(x0)
-        r, q, p, scal = dv.empty(n), dv.empty(n), A.new_vec(), dv.zeros(16)
         ws = dv.workspace()
         g = A.grid
         ws_spmv = ws.spmv_ws(max(_lib.query("pmb_spmv_ws_doubles", g), _lib.query("pmb_elem_ws_doubles", g)))
+        # vectors bound to the plan (persistent: the captured iteration graph holds their addresses)
+        bufs = self._c_bufs
+        if bufs is None or bufs["n"] != n or bufs["A"] is not A:
+            bufs = self._c_bufs = dict(n=n, A=A, b=dv.empty(n), x=A.new_vec(zero=True), r=dv.empty(n), q=dv.empty(n), p=A.new_vec(),
+                                       scal=dv.zeros(16))
+        key = (bytes(desc), ws.red.data_ptr(), ws_spmv.data_ptr())
+        if self._c_plan is None or self._c_plan_key != key:
+            self._drop_plan()
+            plan = C.c_void_p()
+            _lib.call("pmb_pcg_plan_create", C.byref(desc), dv.ptr(bufs["b"]), dv.ptr(bufs["x"]), dv.ptr(bufs["r"]), dv.ptr(bufs["q"]),
+                      dv.ptr(bufs["p"]), dv.ptr(bufs["scal"]), dv.ptr(ws.red), dv.ptr(ws_spmv), C.byref(plan))
+            self._c_plan, self._c_plan_key = plan, key
+        bufs["b"].copy_(b)
+        if x0 is None:
+            bufs["x"].zero_()
+        else:
+            bufs["x"].copy_(x0)
         iters, relres = C.c_int(0), C.c_double(0.0)
         launches0 = _lib.launch_count
-        _lib.call("pmb_pcg_solve", C.byref(desc), dv.ptr(b), dv.ptr(x), dv.ptr(r), dv.ptr(q), dv.ptr(p), float(self.tol), int(self.maxit),
-                  int(self.restart), dv.ptr(scal), dv.ptr(ws.red), dv.ptr(ws_spmv), C.byref(iters), C.byref(relres), dv.stream())
+        _lib.call("pmb_pcg_plan_solve", self._c_plan, float(self.tol), int(self.maxit), int(self.restart), C.byref(iters), C.byref(relres),
+                  dv.stream())
         self.iterations, self.last_residual = int(iters.value), float(relres.value)
         # kernels launched inside the C call: per V-cycle and level 2 steps + 3 (smooth0 / residual, restrict, prolong) + the
         # coarse GEMV; per iteration the product (+ reduce), update, dots, lincomb (bench.py reports gpu_launches)
@@ -512,7 +527,20 @@ class CG(LinearSolver):
         elif self.verbosity >= 1:
             print(f"CG Converged in {self.iterations} iterations and {np.round(time.perf_counter() - tstart, 3)}s, "
                   f"with final (max) residual {self.last_residual}")
+        x = A.new_vec()
+        x.copy_(bufs["x"])
         return x
+
+    def _drop_plan(self):
+        if getattr(self, "_c_plan", None) is not None:
+            _lib.call("pmb_pcg_plan_destroy", self._c_plan)
+        self._c_plan, self._c_plan_key = None, None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
 
     def _solve1(self, b, x0):
         A, M = self.A, self.preconditioner

@@ -1252,6 +1252,10 @@ def test_c_pcg_driver_identical_to_python_driver(pmb, shape, restart, matrix_fre
             results[use_c] = (cold.cpu().numpy(), its_cold, res_cold, warm.cpu().numpy(), cg.iterations, cg.last_residual)
         py, c = results[False], results[True]
         assert py[1] == c[1] and py[4] == c[4], (py[1], c[1], py[4], c[4])
+        # the C driver went through its plan: non-restart iterations were replayed as one captured graph
+        assert cg._c_plan is not None
+        if restart == 50 or py[1] + py[4] > 2 * (py[1] // restart + py[4] // restart + 2) + 2:
+            assert _lib.query("pmb_pcg_plan_graph_replays", cg._c_plan) > 0
         assert py[1] > restart or restart == 50
         assert np.array_equal(py[0], c[0]) and np.array_equal(py[3], c[3])
         assert py[2] == c[2] and py[5] == c[5]
