@@ -19,26 +19,29 @@
 
 enum { SMODE_SPMV = PMB_SPMV, SMODE_RESID = PMB_RESIDUAL, SMODE_JACOBI = PMB_JACOBI };
 constexpr int SYM_SLOTS = 14;
-// Each block is fetched from HBM ONCE and used twice on chip.  (A pure gather -- every node also loading the 13 blocks stored
-// with its lower neighbours -- moves the same 27 blocks per node over the L2 -> SM fabric as the full layout does from HBM and
-// was measured at 0.21 ms against 0.187 ms for the stencil-CSR kernel: the fabric, ~7 TB/s, is the limit, not the DRAM.)
-// A CTA owns SYM_TX x SYM_TY node columns and marches through its chunk of node planes, one thread per node of the
-// current plane.  Per plane a thread
-//   A. reads its 14 blocks (coalesced 8-byte loads: consecutive lanes = consecutive nodes of an x-row) and the x of its 27
-//      neighbours (L1); accumulates its own rows from the diagonal and upper blocks; forms the TRANSPOSED products
-//      B^T x_i for its 13 upper neighbours and leaves each in the shared-memory slot of its target node (4 in-plane
-//      slots, 9 slots for the plane above; one writer per slot and target -> no conflicts, no atomics);
-//      picks up the 9 contributions that the plane below left for it in the previous step;
-//   B. after ONE barrier picks up the 4 in-plane contributions, applies the epilogue and stores.
-// Links that leave the CTA's tile sideways, or come from the plane below the chunk's first, cannot be served on chip: for
-// those (19 % of the lower links of a 32 x 4 tile) the node reads the block stored with its lower neighbour, as in the
-// pure gather.  Fixed summation order: deterministic.
-constexpr int SYM_TX = 32, SYM_TY = 4, SYM_NT = SYM_TX * SYM_TY;
-template <int NDOF>
-struct SymCfg {
-  static constexpr int TIN = 4 * NDOF * SYM_NT, TUP = 9 * NDOF * SYM_NT;   // doubles of one in-plane / upward buffer
-  static constexpr size_t SMEM = sizeof(double) * 2 * (TIN + TUP);
-};
+// Each block is fetched from HBM ONCE and used twice on chip.  Two other designs were built and measured first
+// (256x128x128 bench, level 1, 0.187 ms for the stencil-CSR kernel):
+//   * a pure gather -- every node also loading the 13 blocks stored with its lower neighbours -- moves the same 27 blocks
+//     per node over the L2 -> SM fabric as the full layout does from HBM: 0.21 ms, the fabric (~7 TB/s) is the limit;
+//   * node columns marching in z with the transposed products handed upward through shared memory read only 0.66 GB
+//     from DRAM but exposes one memory round trip per plane to ~1000 resident warps: 0.35 ms, latency bound.
+// Here a CTA owns a BRICK of SYM_BX x SYM_BY x SYM_BZ nodes, one thread per node, all bricks independent.  A thread
+//   * accumulates its own rows from its diagonal block and its 13 upper blocks (coalesced 8-byte loads: consecutive lanes
+//     = consecutive nodes of an x-row; the next block is already in flight while the current one is used);
+//   * forms the TRANSPOSED product B^T x_i of each upper block and adds it to the shared-memory accumulator of the
+//     neighbour it belongs to when that neighbour is a node of the brick -- one direction per phase, so every accumulator
+//     has exactly one writer per phase (a block barrier between phases, no atomics, fixed order: deterministic);
+//   * for the lower neighbours OUTSIDE the brick reads the block stored with the neighbour, as the pure gather would.
+// Measured (same bench): 0.206 ms with 32 x 4 x 2 bricks (0.215 with 32 x 4 x 4, 0.24 with three CTAs of 80 registers) -- the
+// best of the three, still behind the stencil-CSR kernel, whose TMA-streamed contiguous runs reach 0.91 of the HBM peak
+// while 126 interleaved per-thread load streams do not.  The layout therefore stays OFF by default
+// (PMB_SYMMETRIC_STORAGE=1 / DeviceCSR.symmetric_storage enables it); see DESIGN.md section 6c.
+#ifndef PMB_SYM_BY
+#define PMB_SYM_BY 4
+#define PMB_SYM_BZ 2
+#define PMB_SYM_MINB 2
+#endif
+constexpr int SYM_BX = 32, SYM_BY = PMB_SYM_BY, SYM_BZ = PMB_SYM_BZ, SYM_NT = SYM_BX * SYM_BY * SYM_BZ;
 
 __device__ __forceinline__ void sym_dir(int slot, int& di, int& dj, int& dk) {
   const int o = slot + 4;
@@ -118,125 +121,103 @@ __global__ void __launch_bounds__(256) sym_pack_kernel(Geo g, const double* __re
   }
 }
 
-// slot (1..13) -> index among the in-plane upper links (0..3: (di,dj) = (1,0), (-1,1), (0,1), (1,1)) or the upward ones (0..8)
-__host__ __device__ constexpr int sym_sub(int slot) { return slot <= 4 ? slot - 1 : slot - 5; }
-
 template <int NDOF, int MODE>
-__global__ void __launch_bounds__(SYM_NT, 2) sym_kernel(Geo g, int zl, const double* __restrict__ S, const double* __restrict__ x,
+__global__ void __launch_bounds__(SYM_NT, PMB_SYM_MINB) sym_kernel(Geo g, const double* __restrict__ S, const double* __restrict__ x,
                                                         const double* __restrict__ b, const double* __restrict__ diag, double w,
                                                         double* __restrict__ y, const double* __restrict__ dotv,
                                                         double* __restrict__ partials) {
-  using C = SymCfg<NDOF>;
   const long long N = g.nOwned;
-  extern __shared__ __align__(16) double sym_smem[];
-  double* tin = sym_smem;                 // [2][4][NDOF][NT]  in-plane contributions of the current step (by parity of the step)
-  double* tup = sym_smem + 2 * C::TIN;    // [2][9][NDOF][NT]  contributions to the plane above
+  __shared__ double yacc[NDOF][SYM_NT];   // transposed contributions received by the nodes of the brick
   __shared__ double wred[3][SYM_NT / 32];
-  const int tid = threadIdx.x, tx = tid % SYM_TX, ty = tid / SYM_TX;
-  const int i = blockIdx.x * SYM_TX + tx, j = blockIdx.y * SYM_TY + ty;
-  const int kA = blockIdx.z * zl, kB = min(kA + zl, g.NZ);
-  const bool col = i < g.NX && j < g.NY;
+  const int tid = threadIdx.x, tx = tid % SYM_BX, ty = (tid / SYM_BX) % SYM_BY, tz = tid / (SYM_BX * SYM_BY);
+  const int nbx = (g.NX + SYM_BX - 1) / SYM_BX, nby = (g.NY + SYM_BY - 1) / SYM_BY, nbz = (g.NZ + SYM_BZ - 1) / SYM_BZ;
+  const long long nbricks = (long long)nbx * nby * nbz;
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
 
-  for (int k = kA, t = 0; k < kB; ++k, ++t) {
-    const long long ln = ((long long)k * g.NY + j) * g.NX + i;
-    double* tin_w = tin + (t & 1) * C::TIN;
-    double* tup_w = tup + (t & 1) * C::TUP;
-    const double* tup_r = tup + ((t + 1) & 1) * C::TUP;   // written in the previous step
+  for (long long brick = blockIdx.x; brick < nbricks; brick += gridDim.x) {
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+    const int i = bx * SYM_BX + tx, j = by * SYM_BY + ty, k = bz * SYM_BZ + tz;
+    const bool in = i < g.NX && j < g.NY && k < g.NZ;
+    const long long ln = in ? ((long long)k * g.NY + j) * g.NX + i : 0;
     double acc[NDOF], xc[NDOF];
 #pragma unroll
-    for (int d = 0; d < NDOF; ++d) acc[d] = 0.0, xc[d] = 0.0;
-    if (col) {
+    for (int d = 0; d < NDOF; ++d) acc[d] = 0.0, xc[d] = in ? __ldg(x + ln * NDOF + d) : 0.0, yacc[d][tid] = 0.0;
+
+    // block of slot s of this node (zeros are stored for neighbours outside the grid)
+    auto load_block = [&](int slot, double (&blk)[NDOF * NDOF]) {
+      const double* sp = S + (long long)slot * NDOF * NDOF * N + ln;
 #pragma unroll
-      for (int c = 0; c < NDOF; ++c) xc[c] = __ldg(x + ln * NDOF + c);
-      // ---- A. own blocks: diagonal, 13 upper neighbours (+ the transposed products for them), in two batches of 7 slots:
-      //      all loads of a batch are issued before the first is used (two memory round trips per plane instead of 14)
-#pragma unroll
-      for (int bt = 0; bt < 2; ++bt) {
-        double blk[7][NDOF * NDOF], xv[7][NDOF];
-        bool ok[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const int slot = 7 * bt + q, o = slot + 4, dk = o / 9, dj = (o / 3) % 3 - 1, di = o % 3 - 1;
-          const int i2 = i + di, j2 = j + dj, k2 = k + dk;
-          ok[q] = slot == 0 || (i2 >= 0 && i2 < g.NX && j2 >= 0 && j2 < g.NY && k2 < g.NZ);
-          const long long nb = ok[q] ? ln + di + (long long)dj * g.NX + (long long)dk * g.plane : ln;
-          const double* sp = S + (long long)slot * NDOF * NDOF * N + ln;   // (blocks of missing neighbours are stored as zeros)
-#pragma unroll
-          for (int e = 0; e < NDOF * NDOF; ++e) blk[q][e] = __ldg(sp + (long long)e * N);
-#pragma unroll
-          for (int c = 0; c < NDOF; ++c) xv[q][c] = __ldg(x + nb * NDOF + c);
-        }
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const int slot = 7 * bt + q, o = slot + 4, dk = o / 9, dj = (o / 3) % 3 - 1, di = o % 3 - 1;
-#pragma unroll
-          for (int d = 0; d < NDOF; ++d)
-#pragma unroll
-            for (int c = 0; c < NDOF; ++c) acc[d] = fma(blk[q][d * NDOF + c], xv[q][c], acc[d]);
-          if (slot > 0 && ok[q]) {
-            // the neighbour's rows take B^T x_i: on chip when the neighbour is a node of this tile (and, upward, of this chunk)
-            const int tx2 = tx + di, ty2 = ty + dj;
-            if (tx2 >= 0 && tx2 < SYM_TX && ty2 >= 0 && ty2 < SYM_TY && (dk == 0 || k + dk < kB)) {
-              double* dst = (dk == 0 ? tin_w : tup_w) + sym_sub(slot) * NDOF * SYM_NT + ty2 * SYM_TX + tx2;
-#pragma unroll
-              for (int c = 0; c < NDOF; ++c) {
-                double tv = 0.0;
-#pragma unroll
-                for (int d = 0; d < NDOF; ++d) tv = fma(blk[q][d * NDOF + c], xc[d], tv);
-                dst[c * SYM_NT] = tv;
-              }
-            }
-          }
-        }
-      }
-      // ---- lower neighbours: on-chip contributions of the plane below (left in the previous step), or -- when the link
-      //      leaves the tile / the chunk -- the block stored with the neighbour, transposed
+      for (int e = 0; e < NDOF * NDOF; ++e) blk[e] = in ? __ldg(sp + (long long)e * N) : 0.0;
+    };
+    double cur[NDOF * NDOF], nxt[NDOF * NDOF];
+    load_block(0, cur);
+    load_block(1, nxt);
+    // ---- lower neighbours outside the brick: the block stored with the neighbour, transposed (issued early: independent)
+    if (in) {
 #pragma unroll
       for (int slot = 1; slot < SYM_SLOTS; ++slot) {
         const int o = slot + 4, dk = o / 9, dj = (o / 3) % 3 - 1, di = o % 3 - 1;
         const int i2 = i - di, j2 = j - dj, k2 = k - dk;
-        if (i2 >= 0 && i2 < g.NX && j2 >= 0 && j2 < g.NY && k2 >= 0) {
-          const int tx2 = tx - di, ty2 = ty - dj;
-          const bool onchip = tx2 >= 0 && tx2 < SYM_TX && ty2 >= 0 && ty2 < SYM_TY && (dk == 0 || k2 >= kA);
-          if (!onchip) {
-            const long long nb = ln - di - (long long)dj * g.NX - (long long)dk * g.plane;
-            const double* sp = S + (long long)slot * NDOF * NDOF * N + nb;
-            double xv[NDOF];
+        const int tx2 = tx - di, ty2 = ty - dj, tz2 = tz - dk;
+        const bool inbrick = tx2 >= 0 && tx2 < SYM_BX && ty2 >= 0 && ty2 < SYM_BY && tz2 >= 0;   // (tz2 < SYM_BZ: dk >= 0)
+        if (!inbrick && i2 >= 0 && i2 < g.NX && j2 >= 0 && j2 < g.NY && k2 >= 0) {
+          const long long nb = ln - di - (long long)dj * g.NX - (long long)dk * g.plane;
+          const double* sp = S + (long long)slot * NDOF * NDOF * N + nb;
+          double xv[NDOF];
 #pragma unroll
-            for (int c = 0; c < NDOF; ++c) xv[c] = __ldg(x + nb * NDOF + c);
+          for (int c = 0; c < NDOF; ++c) xv[c] = __ldg(x + nb * NDOF + c);
 #pragma unroll
-            for (int c = 0; c < NDOF; ++c)
+          for (int c = 0; c < NDOF; ++c)
 #pragma unroll
-              for (int d = 0; d < NDOF; ++d) acc[d] = fma(__ldg(sp + (long long)(c * NDOF + d) * N), xv[c], acc[d]);
-          } else if (dk == 1) {
-            const double* src = tup_r + sym_sub(slot) * NDOF * SYM_NT + tid;
+            for (int d = 0; d < NDOF; ++d) acc[d] = fma(__ldg(sp + (long long)(c * NDOF + d) * N), xv[c], acc[d]);
+        }
+      }
+      // diagonal block
 #pragma unroll
-            for (int d = 0; d < NDOF; ++d) acc[d] += src[d * SYM_NT];
+      for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) acc[d] = fma(cur[d * NDOF + c], xc[c], acc[d]);
+    }
+    __syncthreads();   // every accumulator of the brick is zeroed
+    // ---- the 13 upper directions, one phase each
+#pragma unroll
+    for (int slot = 1; slot < SYM_SLOTS; ++slot) {
+      const int o = slot + 4, dk = o / 9, dj = (o / 3) % 3 - 1, di = o % 3 - 1;
+#pragma unroll
+      for (int e = 0; e < NDOF * NDOF; ++e) cur[e] = nxt[e];
+      if (slot + 1 < SYM_SLOTS) load_block(slot + 1, nxt);
+      const int i2 = i + di, j2 = j + dj, k2 = k + dk;
+      if (in && i2 >= 0 && i2 < g.NX && j2 < g.NY && k2 < g.NZ) {   // (j2 >= 0: an upper direction with dj = -1 has dk = 1 ... checked below)
+        if (j2 >= 0) {
+          const long long nb = ln + di + (long long)dj * g.NX + (long long)dk * g.plane;
+#pragma unroll
+          for (int d = 0; d < NDOF; ++d)
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) acc[d] = fma(cur[d * NDOF + c], __ldg(x + nb * NDOF + c), acc[d]);
+          const int tx2 = tx + di, ty2 = ty + dj, tz2 = tz + dk;
+          if (tx2 >= 0 && tx2 < SYM_BX && ty2 >= 0 && ty2 < SYM_BY && tz2 < SYM_BZ) {
+            const int tgt = (tz2 * SYM_BY + ty2) * SYM_BX + tx2;
+#pragma unroll
+            for (int c = 0; c < NDOF; ++c) {
+              double tv = 0.0;
+#pragma unroll
+              for (int d = 0; d < NDOF; ++d) tv = fma(cur[d * NDOF + c], xc[d], tv);
+              yacc[c][tgt] += tv;
+            }
           }
         }
       }
+      __syncthreads();   // one writer per accumulator and phase
     }
-    __syncthreads();
-    // ---- B. in-plane contributions of this step, epilogue
-    if (col) {
-#pragma unroll
-      for (int slot = 1; slot <= 4; ++slot) {
-        const int o = slot + 4, dj = (o / 3) % 3 - 1, di = o % 3 - 1;
-        const int tx2 = tx - di, ty2 = ty - dj;
-        if (tx2 >= 0 && tx2 < SYM_TX && ty2 >= 0 && ty2 < SYM_TY && i - di < g.NX && j - dj < g.NY) {   // (i - di, j - dj >= 0: inside the tile)
-          const double* src = tin_w + sym_sub(slot) * NDOF * SYM_NT + tid;
-#pragma unroll
-          for (int d = 0; d < NDOF; ++d) acc[d] += src[d * SYM_NT];
-        }
-      }
+    if (in) {
 #pragma unroll
       for (int d = 0; d < NDOF; ++d) {
         const long long r = ln * NDOF + d;
+        const double ax = acc[d] + yacc[d][tid];
         double out;
-        if (MODE == SMODE_SPMV) out = acc[d];
-        else if (MODE == SMODE_RESID) out = b[r] - acc[d];
-        else out = xc[d] + w * ((b[r] - acc[d]) / diag[r]);
+        if (MODE == SMODE_SPMV) out = ax;
+        else if (MODE == SMODE_RESID) out = b[r] - ax;
+        else out = xc[d] + w * ((b[r] - ax) / diag[r]);
         y[r] = out;
         if (partials) {
           const double dvv = dotv ? dotv[r] : 0.0;
@@ -246,6 +227,7 @@ __global__ void __launch_bounds__(SYM_NT, 2) sym_kernel(Geo g, int zl, const dou
         }
       }
     }
+    __syncthreads();   // the accumulators are read before the next brick zeroes them
   }
   if (partials) {
     d0 = warp_sum(d0);
@@ -256,10 +238,9 @@ __global__ void __launch_bounds__(SYM_NT, 2) sym_kernel(Geo g, int zl, const dou
     if (tid == 0) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int v = 0; v < SYM_NT / 32; ++v) s0 += wred[0][v], s1 += wred[1][v], s2 += wred[2][v];
-      const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      partials[3 * bid] = s0;
-      partials[3 * bid + 1] = s1;
-      partials[3 * bid + 2] = s2;
+      partials[3 * (long long)blockIdx.x] = s0;
+      partials[3 * (long long)blockIdx.x + 1] = s1;
+      partials[3 * (long long)blockIdx.x + 2] = s2;
     }
   }
 }
@@ -300,42 +281,16 @@ extern "C" int pmb_sym_pack(const pmb_grid* p, const double* data, double* S, un
   return 0;
 }
 
-// planes per CTA: at most 4 CTAs per SM worth of partial triples (pmb_spmv_ws_doubles), few CTAs lost to the last wave, short
-// chunks cost one gathered plane each
-static int sym_zl(const Geo& g, long long tiles, int sms) {
-  const long long slots = 2LL * sms, cap = 4LL * sms;
-  int best = g.NZ;
-  double best_cost = 1e300;
-  for (int chunks = 1; chunks <= g.NZ; ++chunks) {
-    const int zl = (g.NZ + chunks - 1) / chunks;
-    const long long ctas = tiles * ((g.NZ + zl - 1) / zl);
-    if (ctas > cap && chunks > 1) break;
-    const long long waves = (ctas + slots - 1) / slots;
-    const double cost = (double)waves * (zl + 0.35);   // the first plane of a chunk gathers 9 of its 27 blocks a second time
-    if (cost < best_cost - 1e-12) best_cost = cost, best = zl;
-  }
-  return best;
-}
-
 template <int NDOF, int MODE>
 static int launch_sym(const Geo& g, const double* S, const double* x, const double* b, const double* diag, double w, double* y,
                       const double* dotv, double* dot_out, double* ws, cudaStream_t st) {
-  using C = SymCfg<NDOF>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sym_kernel<NDOF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return pmb_set_error("sym_kernel attribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
-  const int nbx = (g.NX + SYM_TX - 1) / SYM_TX, nby = (g.NY + SYM_TY - 1) / SYM_TY;
-  const int zl = sym_zl(g, (long long)nbx * nby, sym_sm_count());
-  const int nbz = (g.NZ + zl - 1) / zl;
-  PMB_REQUIRE(nby <= 65535 && nbz <= 65535, "pmb_sym_spmv: grid too large");
-  PMB_REQUIRE(!dot_out || (long long)nbx * nby * nbz <= 4LL * sym_sm_count(), "pmb_sym_spmv: grid too large for the fused dot products");
-  sym_kernel<NDOF, MODE><<<dim3(nbx, nby, nbz), SYM_NT, C::SMEM, st>>>(g, zl, S, x, b, diag, w, y, dotv, dot_out ? ws : nullptr);
+  const long long nbricks = (long long)((g.NX + SYM_BX - 1) / SYM_BX) * ((g.NY + SYM_BY - 1) / SYM_BY) * ((g.NZ + SYM_BZ - 1) / SYM_BZ);
+  const long long cap = 4LL * sym_sm_count();   // == pmb_spmv_ws_doubles() / 3 partial triples
+  const int grid = (int)(dot_out ? (nbricks < cap ? nbricks : cap) : (nbricks < 2147483647LL ? nbricks : 2147483647LL));
+  sym_kernel<NDOF, MODE><<<grid, SYM_NT, 0, st>>>(g, S, x, b, diag, w, y, dotv, dot_out ? ws : nullptr);
   PMB_CHECK_LAUNCH("pmb_sym_spmv");
   if (dot_out) {
-    reduce_triples_kernel<<<1, 1024, 0, st>>>(ws, (long long)nbx * nby * nbz, dot_out);
+    reduce_triples_kernel<<<1, 1024, 0, st>>>(ws, grid, dot_out);
     PMB_CHECK_LAUNCH("pmb_sym_spmv(reduce)");
   }
   return 0;

@@ -138,8 +138,7 @@ class DeviceCSR:
         g = self.grid
         self._sym_valid = False
         if (not DeviceCSR.symmetric_storage or self.level < 1 or self.comm is not None or g.nz == 0 or g.kz0 != 0 or g.nzl != g.nz + 1
-                or self.n // g.ndof < DeviceCSR.symmetric_min_nodes or torch.cuda.is_current_stream_capturing()
-                or ((g.nx + 32) // 32) * ((g.ny + 4) // 4) > 4 * dv.sm_count()):  # one partial triple per CTA (fused dots)
+                or self.n // g.ndof < DeviceCSR.symmetric_min_nodes or torch.cuda.is_current_stream_capturing()):
             return False
         if self._sym is None:
             self._sym = dv.empty(_lib.query("pmb_sym_doubles", g))

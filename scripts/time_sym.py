@@ -38,6 +38,7 @@ def main():
     asm = (pmb.AssembleStiffness if ndof == 3 else pmb.AssemblePoisson)(dom, bc=bc)
     x = torch.rand(dom.nel, dtype=torch.float64, device="cuda") * 0.9 + 0.1
     K = asm(x)
+    DeviceCSR.symmetric_storage = True  # (off by default: build the symmetric copy for this measurement)
     mg = pmb.solvers.auto_multigrid(dom)[0]
     mg.update(K)
     A1 = mg.Ac
