@@ -1615,8 +1615,6 @@ static int launch_elem(const Geo& g, const pmb_elem_op* op, const double* x, con
       switch (variant - 8) {
         case 0: launch(std::integral_constant<int, 0>{}); break;
         case 1: launch(std::integral_constant<int, 1>{}); break;
-        case 2: launch(std::integral_constant<int, 2>{}); break;
-        case 3: launch(std::integral_constant<int, 3>{}); break;
       }
       if (rc) return rc;
     } else if (variant == 4 || variant == 5) {

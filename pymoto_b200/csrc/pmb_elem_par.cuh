@@ -444,8 +444,10 @@ __global__ void __launch_bounds__(PAR_EX* EY, MINB)
 struct ParLaunchCfg {
   int ey, minb;
 };
-constexpr int PAR_NCFG = 4;
-constexpr ParLaunchCfg PAR_CFG[PAR_NCFG] = {{8, 2}, {16, 1}, {12, 1}, {10, 1}};
+// (measured at 256x128x128, ndof 3: 32 x 8 columns, 2 CTAs / SM 0.254 ms; 32 x 16, 1 CTA / SM 0.254 ms; 12 / 10 warps per
+//  SM -- 32 x 12 or 32 x 10 columns in one CTA -- 0.30 ms: the kernel is latency bound and wants every warp it can get)
+constexpr int PAR_NCFG = 2;
+constexpr ParLaunchCfg PAR_CFG[PAR_NCFG] = {{8, 2}, {16, 1}};
 
 // planes per CTA: few CTAs lost to the last wave, little redundant layer work (every CTA computes one extra layer)
 static int par_zl(const Geo& g, int ey, int ctas_per_sm, int sms) {
