@@ -200,13 +200,17 @@ def design_updates(rank, world):
         # elements sit on their move limits the volume is piecewise constant in the multiplier and can hit the target EXACTLY:
         # the branch then depends on the last bit of the sum (summation order), and the multiplier -- hence the design -- moves
         # by the width of the plateau, O(1e-4) (observed: inputs equal to 1e-13, designs 5e-5 apart, uniformly).  The first
-        # update is compared tightly, the following ones at the bisection's own resolution.
-        tol_x, tol_c = (1e-6, 1e-6) if it == 0 else (1e-3, 1e-3)
+        # update is compared tightly, the following ones at the bisection's own resolution: the loop stops at an ABSOLUTE
+        # bracket width of 1e-4 on the multiplier, which on the tall 16x8x64 grid of the 8-rank run (multiplier ~ 1e-2) is a
+        # relative 1e-2, i.e. designs up to ~5e-3 apart (observed 3.2e-3 with inputs equal to 1e-13); the mean density -- what the
+        # bisection actually controls -- must still agree to its tolerance.
+        tol_x, tol_c = (1e-6, 1e-6) if it == 0 else (5e-3, 1e-3)
         if rank == 0:
             print(f"[dist_check]   OC update {it}: objective {g!r} (oracle {c_ref!r}, rel {abs(g - c_ref) / abs(c_ref):.2e}), "
                   f"max |x - x_oracle| = {np.abs(xg - x_ref).max():.2e}, mean {np.abs(xg - x_ref).mean():.2e}")
         assert abs(g - c_ref) <= tol_c * abs(c_ref), ("OC objective", it, g, c_ref)
         assert np.abs(xg - x_ref).max() <= tol_x, ("OC design", it, np.abs(xg - x_ref).max())
+        assert abs(xg.mean() - x_ref.mean()) <= 5e-4, ("OC volume", it, xg.mean(), x_ref.mean())
     if rank == 0:
         print(f"[dist_check] OC on {world} slabs: 3 updates match the oracle (first 1e-6, then the bisection tolerance), last objective {g!r}")
     pmb.slab.reset()
