@@ -533,7 +533,7 @@ def run_b200(args, full):
     barrier()
     sampler.begin()
     launches0, stats0 = _lib.launch_count, dict(_lib.call_stats)
-    comm0 = (chain.ctx.comm.exchanges, chain.ctx.comm.allreduces)
+    comm0 = (chain.ctx.comm.exchanges, chain.ctx.comm.allreduces, getattr(chain.ctx.comm, "fast_allreduces", 0))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     cg_its, compl = [], []
     ev[0].record()
@@ -545,11 +545,15 @@ def run_b200(args, full):
     barrier()
     sampler.end()
     clocks = sampler.stop()
+    if world > 1:
+        chain.ctx.comm.check_peer_timeouts()  # a one-launch exchange that gave up waiting would make the timing meaningless
     launches = _lib.launch_count - launches0
     stats = {k: v - stats0.get(k, 0) for k, v in _lib.call_stats.items() if v - stats0.get(k, 0) > 0}
     comm_counts = {"halo_exchanges_per_step": (chain.ctx.comm.exchanges - comm0[0]) / K,
                    "allreduces_per_step": (chain.ctx.comm.allreduces - comm0[1]) / K,
-                   "launches_per_step": launches / K} if world > 1 else None
+                   "launches_per_step": launches / K,
+                   "one_launch_peer_exchange": bool(getattr(chain.ctx.comm, "fused", False)),
+                   "one_launch_peer_allreduces_per_step": (chain.ctx.comm.fast_allreduces - comm0[2]) / K} if world > 1 else None
     total_ms = maxreduce(ev[0].elapsed_time(ev[K]))
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
     # one slab-decomposed job over all ranks.  Weak scaling: the grid grows with the rank count, so the whole-job
@@ -786,8 +790,10 @@ def run_b200(args, full):
                                    (f"matrix-free (layout {gen.variant})" if was_mf and not args.csr else "streamed from the assembled CSR values"),
                        "l2": "inputs larger than L2 (8.2 GB of matrix values written per step, > 100 MB vectors per operator application)",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"{world} z-slabs ({chain.ctx.part.n_dist} split multigrid levels, coarser levels replicated), peer-memory halo "
-                       "mailboxes + NCCL all-reduce; value = iterations/s x dof / 12.83M (weak scaling: a NORMALISED number, "
+                       f"{world} z-slabs ({chain.ctx.part.n_dist} split multigrid levels, coarser levels replicated), " +
+                       ("halo exchange and dot-product all-reduce as one-launch kernels over NVLink peer memory (pmb_peer_*)"
+                        if getattr(chain.ctx.comm, "fused", False) else "peer-memory halo mailboxes + NCCL all-reduce") +
+                       "; value = iterations/s x dof / 12.83M (weak scaling: a NORMALISED number, "
                        "iters_per_sec_this_grid is the raw rate)",
                        "iters_per_sec_this_grid": iters_per_sec},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity": parity, "comm": comm_counts,

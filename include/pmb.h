@@ -240,6 +240,43 @@ int pmb_vec_div(long long n, const double* a, const double* b, double* out, void
  * symmetric memory: the stores then travel over NVLink).  Any (src, dst) pair with a NULL member is skipped. */
 int pmb_halo_copy2(long long n, const double* src0, double* dst0, const double* src1, double* dst1, void* stream);
 
+/* ---- exchange steps over peer memory, ONE launch each (the Python host's default on z-slabs).  All pointers named "peer"
+ * are this process's mappings of another rank's symmetric-memory allocation (e.g. torch symmetric memory, cuMemMap of an
+ * exported handle): stores to them travel over NVLink.  No communicator, no host involvement, no separate barrier launch,
+ * capturable in a CUDA graph.  Transport: every double travels as a 16-byte unit {low word, exchange number, high word, exchange
+ * number}; the receiver polls its own memory until both numbers match (no fence, no flag round trip: one launch + one NVLink
+ * store flight per exchange).  Every rank must issue the same sequence of these calls on one stream.  `ctl` is ordinary device
+ * memory of the calling rank; mailboxes, tables and ctl are zeroed once (then a host barrier) before the first call.
+ * pmb_peer_halo_exchange: send `n` doubles from send_lo / send_hi to the lower / upper neighbour and receive what they send
+ * into recv_lo / recv_hi.  Any of the four data pointers may be NULL (one-way exchanges); a header unit is still exchanged with
+ * both neighbours, which is what makes two alternating mailbox slots enough.  Replaces pack kernel + device barrier + unpack
+ * kernel.  ctl[2] != 0 (also reduce ctl[1]): a neighbour never arrived within ~60 s -- the number of the first such exchange;
+ * results are invalid from then on and later calls no longer wait. */
+typedef struct pmb_peer_halo {
+  double* box;     /* this rank's mailbox: pmb_peer_halo_box_doubles(cap) doubles, 16-byte aligned */
+  double* box_lo;  /* the lower / upper neighbour's mailbox (peer pointers), NULL at the ends of the domain */
+  double* box_hi;
+  unsigned long long* ctl; /* 3 words of this rank's device memory: exchange counter, CTA counter, first timed-out exchange */
+  long long cap;   /* largest n */
+} pmb_peer_halo;
+long long pmb_peer_halo_box_doubles(long long cap);
+int pmb_peer_halo_exchange(const pmb_peer_halo* h, long long n, const double* send_lo, const double* send_hi,
+                           double* recv_lo, double* recv_hi, void* stream);
+/* pmb_peer_allreduce: in-place sum (op 0) or maximum (op 1) of count <= PMB_PEER_COUNT_MAX device doubles over all ranks: every
+ * rank stores its values into its column of every rank's table, the columns are combined in rank order (identical bits on every
+ * rank, run-to-run deterministic).  slots[p]: rank p's table of pmb_peer_reduce_table_doubles(world) doubles ([rank] = the
+ * caller's own).  Replaces the NCCL all-reduce of the CG / LDAS dot products (pymoto/solvers/iterative.py:365-398 evaluates
+ * them with numpy on one process). */
+#define PMB_PEER_MAX 16
+#define PMB_PEER_COUNT_MAX 16
+typedef struct pmb_peer_reduce {
+  int world, rank;
+  double* slots[PMB_PEER_MAX];
+  unsigned long long* ctl; /* 2 words of this rank's device memory: all-reduce counter, first timed-out all-reduce */
+} pmb_peer_reduce;
+long long pmb_peer_reduce_table_doubles(int world);
+int pmb_peer_allreduce(const pmb_peer_reduce* r, double* val, int count, int op, void* stream);
+
 /* ---- slab communication over NCCL: lets a host without torch.distributed drive the z-slab path.  NCCL is
  * bound at run time (dlopen libnccl.so.2); without it these return an error.  One handle per process / GPU, made from a
  * 128-byte ncclUniqueId that rank 0 creates (pmb_comm_unique_id) and the caller distributes.  z-neighbours are rank +- 1.

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpmb.so")
-SOURCES = ["pmb_api.cu", "pmb_assembly.cu", "pmb_spmv.cu", "pmb_symstore.cu", "pmb_multigrid.cu", "pmb_vector.cu", "pmb_filter.cu", "pmb_elem.cu", "pmb_optim.cu", "pmb_solver.cu", "pmb_probe.cu", "pmb_comm.cu"]
+SOURCES = ["pmb_api.cu", "pmb_assembly.cu", "pmb_spmv.cu", "pmb_symstore.cu", "pmb_multigrid.cu", "pmb_vector.cu", "pmb_filter.cu", "pmb_elem.cu", "pmb_optim.cu", "pmb_solver.cu", "pmb_probe.cu", "pmb_comm.cu", "pmb_peer.cu"]
 
 
 def needs_build():

@@ -70,6 +70,22 @@ class MgDesc(C.Structure):
     _fields_ = [("nlevels", C.c_int), ("level", MgLevel * MAX_LEVELS), ("coarse_grid", Grid), ("coarse_inv", C.c_void_p),
                 ("coarse_out", C.c_void_p), ("gen", ElemOp)]
 
+PEER_MAX = 16  # PMB_PEER_MAX
+PEER_COUNT_MAX = 16  # PMB_PEER_COUNT_MAX
+
+
+class PeerHalo(C.Structure):
+    """Mirror of ``pmb_peer_halo``: mailboxes of the one-launch halo exchange over peer memory."""
+
+    _fields_ = [("box", C.c_void_p), ("box_lo", C.c_void_p), ("box_hi", C.c_void_p), ("ctl", C.c_void_p), ("cap", C.c_longlong)]
+
+
+class PeerReduce(C.Structure):
+    """Mirror of ``pmb_peer_reduce``: tables of the one-launch small all-reduce over peer memory."""
+
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("slots", C.c_void_p * PEER_MAX), ("ctl", C.c_void_p)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _D = C.c_double
@@ -124,6 +140,10 @@ SIGNATURES = {
     "pmb_stencil_corr": (_I, [_I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     "pmb_vec_div": (_I, [_LL, _P, _P, _P, _P]),
     "pmb_halo_copy2": (_I, [_LL, _P, _P, _P, _P, _P]),
+    "pmb_peer_halo_box_doubles": (_LL, [_LL]),
+    "pmb_peer_reduce_table_doubles": (_LL, [_I]),
+    "pmb_peer_halo_exchange": (_I, [C.POINTER(PeerHalo), _LL, _P, _P, _P, _P, _P]),
+    "pmb_peer_allreduce": (_I, [C.POINTER(PeerReduce), _P, _I, _I, _P]),
     "pmb_comm_unique_id": (_I, [_P]),
     "pmb_comm_init": (_I, [_P, _I, _I, C.POINTER(C.c_void_p)]),
     "pmb_comm_destroy": (_I, [_P]),

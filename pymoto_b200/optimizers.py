@@ -25,12 +25,9 @@ def _comm():
 
 def _allreduce(t, op="sum"):
     """In-place all-reduce of a small device tensor over the slabs (no-op on one GPU)."""
-    import torch.distributed as dist
-
     comm = _comm()
     if comm is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=comm.group)
-        comm.allreduces += 1
+        comm.allreduce_(t, op)
     return t
 
 

@@ -96,7 +96,10 @@ class SlabComm:
         self.exchanges = 0
         self.allreduces = 0
         self.fast = False  # symmetric-memory mailboxes enabled (CUDA + NCCL only)
+        self.fused = False  # one-launch exchange kernels (pmb_peer_*) on top of them
         self.fast_exchanges = 0
+        self.fast_allreduces = 0
+        self._fx_red_max = 16 if os.environ.get("PMB_PEER_ALLREDUCE", "1") != "0" else 0
 
     def enable_mailboxes(self, max_doubles, device):
         """Halo exchange through symmetric memory instead of NCCL send/recv: every rank gets a mailbox of
@@ -121,7 +124,50 @@ class SlabComm:
         self._slot = 0
         self._gslot = 0
         self.fast = True
+        self.fused = False
+        if os.environ.get("PMB_PEER_FUSED", "1") != "0" and p.world <= 16:
+            self._enable_fused(device)
         return True
+
+    def _enable_fused(self, device):
+        """One-launch exchange steps (``pmb_peer_halo_exchange`` / ``pmb_peer_allreduce``): a second symmetric allocation holds
+        2 mailbox slots x 2 directions and the tables of the small all-reduce (every double travels as a 16-byte unit that
+        carries the exchange number, so there are no separate flags and no barrier); the kernels number the exchanges themselves
+        (a counter in local device memory), so eager launches and CUDA-graph replays share the slots."""
+        import ctypes as C
+
+        from . import _lib
+
+        p, cap, W = self.part, self._cap, self.part.world
+        n_box, n_tab = _lib.query("pmb_peer_halo_box_doubles", cap), _lib.query("pmb_peer_reduce_table_doubles", W)
+        total = n_box + n_tab
+        self._fx = self._symm.empty(total, dtype=torch.float64, device=device)  # all-zero bits = exchange number 0 in every unit
+        self._fx.zero_()
+        self._fx_ctl = torch.zeros(8, dtype=torch.int64, device=device)
+        torch.cuda.synchronize()
+        self._fx_hdl = self._symm.rendezvous(self._fx, dist.group.WORLD if self.group is None else self.group)
+        dist.barrier(group=self.group)  # nobody stores into a peer's mailbox before that peer has zeroed it
+        base = [self._fx_hdl.get_buffer(r, (total,), torch.float64).data_ptr() for r in range(W)]
+        self._fx_halo = _lib.PeerHalo(base[p.rank], base[p.lower] if p.lower is not None else None,
+                                      base[p.upper] if p.upper is not None else None, self._fx_ctl.data_ptr(), cap)
+        red = _lib.PeerReduce()
+        red.world, red.rank, red.ctl = W, p.rank, self._fx_ctl.data_ptr() + 8 * 4
+        for r in range(W):
+            red.slots[r] = base[r] + 8 * n_box
+        self._fx_red = red
+        self._fx_byref = (C.byref(self._fx_halo), C.byref(self._fx_red))
+        self.fused = True
+
+    def check_peer_timeouts(self):
+        """Synchronise and raise if a one-launch exchange kernel ever gave up waiting for a peer (its results are invalid)."""
+        if self.fused:
+            torch.cuda.synchronize()
+            ctl = self._fx_ctl.cpu()
+            if int(ctl[2]) or int(ctl[5]):
+                from . import _lib
+
+                raise _lib.PmbError(f"rank {self.part.rank}: a peer never arrived (halo exchange #{int(ctl[2])}, all-reduce "
+                                    f"#{int(ctl[5])} timed out): the ranks issued different exchange sequences, or a rank died")
 
     # ---- CUDA-graph capture of code that exchanges halos (the slab V-cycle)
     def begin_capture(self):
@@ -149,6 +195,8 @@ class SlabComm:
         st = torch.cuda.current_stream().cuda_stream
         n, src = local.numel(), local.data_ptr()
         dsts = [p.data_ptr() + 8 * offset for p in peers]
+        if self.fused:  # the one-launch halo exchanges synchronise neighbours only: before overwriting every rank's copy make
+            hdl.barrier(channel=0)  # sure every rank is done reading the previous one (the old exchanges were global barriers)
         for i in range(0, len(dsts), 2):
             _lib.call("pmb_halo_copy2", n, src, dsts[i], src if i + 1 < len(dsts) else None, dsts[i + 1] if i + 1 < len(dsts) else None, st)
         hdl.barrier(channel=0)
@@ -159,13 +207,19 @@ class SlabComm:
 
         p = self.part
         st = torch.cuda.current_stream().cuda_stream
+        b0 = base.data_ptr() + 8 * own_offset  # first owned entry
+        if self.fused:  # pack, publish, wait, unpack in one launch; `upper` = my upper halo is wanted = bottom planes travel down
+            _lib.call("pmb_peer_halo_exchange", self._fx_byref[0], n, b0 if upper else None, b0 + 8 * (own_len - n) if lower else None,
+                      b0 - 8 * n if lower else None, b0 + 8 * own_len if upper else None, st)
+            self.exchanges += 1
+            self.fast_exchanges += 1
+            return
         if torch.cuda.is_current_stream_capturing():
             o = (2 + (self._gslot & 1)) * 2 * self._cap
             self._gslot += 1
         else:
             o = (self._slot & 1) * 2 * self._cap
             self._slot += 1
-        b0 = base.data_ptr() + 8 * own_offset  # first owned entry
         # box layout per slot: [0, cap) = planes coming from the rank below, [cap, 2 cap) = from the rank above
         # `upper` = I want my upper halo filled = every rank sends its bottom planes down; `lower` = top planes go up
         src0 = dst0 = src1 = dst1 = None
@@ -239,9 +293,19 @@ class SlabComm:
         for r in reqs:
             r.wait()
 
-    def allreduce_(self, t):
+    def allreduce_(self, t, op="sum"):
+        """In-place sum (or maximum) over the slabs.  Up to 16 doubles on the device go through the one-launch peer-memory
+        kernel (combined in rank order: identical bits on every rank), everything else through the process group."""
         if self.active:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if (getattr(self, "fused", False) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                    and 1 <= t.numel() <= self._fx_red_max):
+                from . import _lib
+
+                _lib.call("pmb_peer_allreduce", self._fx_byref[1], t.data_ptr(), t.numel(), 0 if op == "sum" else 1,
+                          torch.cuda.current_stream().cuda_stream)
+                self.fast_allreduces += 1
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
             self.allreduces += 1
         return t
 
@@ -282,13 +346,17 @@ class SlabContext:
 _context = None
 
 
-def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=1_000_000, mailboxes=True):
+def init(domain, n_levels=1, group=None, min_planes=4, force_n_dist=None, ndof=3, min_dofs=None, mailboxes=True):
     """Decompose ``domain`` in z over the ranks of the (default) process group. Call after init_process_group.
 
     ``n_levels`` = number of matrices in the multigrid hierarchy (GeometricMultigrid operators + 1).  Levels with
-    fewer than ``min_dofs`` unknowns or fewer than ``min_planes`` node planes per rank are replicated on every rank.
+    fewer than ``min_dofs`` unknowns (default 200 000, ``PMB_SLAB_MIN_DOFS``: with 4-7 us per one-launch halo exchange a level
+    of that size is cheaper split than replicated, measured) or fewer than ``min_planes`` node planes per rank are replicated
+    on every rank.
     """
     global _context
+    if min_dofs is None:
+        min_dofs = int(os.environ.get("PMB_SLAB_MIN_DOFS", 200_000))
     rank, world = world_from_env()
     nx, ny, nz = int(domain.nelx), int(domain.nely), int(getattr(domain, "nelz", 0) or 0)
     level_dofs = [ndof * ((nx >> l) + 1) * ((ny >> l) + 1) * ((nz >> l) + 1) for l in range(max(n_levels, 1))]

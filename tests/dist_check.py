@@ -31,6 +31,7 @@ def main():
     from oracle import Grid
     from oracle.chain import ComplianceProblem
 
+    peer_primitives(rank, world)
     cases = [((32, 16, 16), 4, dict(min_planes=2, min_dofs=0)),      # 2 split levels + replicated tail
              ((32, 16, 16), 4, dict(min_planes=2, min_dofs=10 ** 9)),  # only the finest level split
              ((16, 8, 8 * world), 4, dict(min_planes=2, min_dofs=0))]
@@ -92,6 +93,7 @@ def main():
         assert err_c <= 1e-6, err_c
         assert err_dx <= 1e-6, err_dx
         assert abs(cg.iterations - P.cg.iterations) <= 1
+        ctx.comm.check_peer_timeouts()
         pmb.slab.reset()
     design_updates(rank, world)
     filterconv_slabs(rank, world)
@@ -99,6 +101,93 @@ def main():
     if rank == 0:
         print("[dist_check] OK")
     dist.destroy_process_group()
+
+
+def peer_primitives(rank, world):
+    """The one-launch exchange steps (pmb_peer_halo_exchange / pmb_peer_allreduce) on their own: a seeded sequence of two-way
+    and one-way halo exchanges of varying size with rank- and step-dependent data, eager and replayed from a CUDA graph,
+    interleaved with small all-reduces; every received plane and every reduced value is checked exactly."""
+    import pymoto_b200 as pmb
+
+    nx, ny, nz = 12, 6, 4 * world
+    dom = pmb.VoxelDomain(nx, ny, nz)
+    ctx = pmb.slab.init(dom, n_levels=1)
+    comm = ctx.comm
+    if not getattr(comm, "fused", False):
+        if rank == 0:
+            print("[dist_check] peer primitives: one-launch exchange kernels not enabled (PMB_PEER_FUSED=0 or no symmetric memory)")
+        pmb.slab.reset()
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plane = ((nx + 1) * (ny + 1) * 3) // 2  # two of these fit a mailbox slot
+    own = 4 * plane
+    rng = np.random.default_rng(11)  # the same sequence on every rank
+
+    def pattern(r, step):
+        return (torch.arange(own, dtype=torch.float64, device=dev) * 1e-3 + 1000.0 * r + 7.0 * step)
+
+    buf = torch.zeros(own + 4 * plane, dtype=torch.float64, device=dev)
+    off = 2 * plane
+
+    def run(step, lower, upper, width):
+        n = plane * width
+        buf.fill_(-1.0)
+        buf[off:off + own] = pattern(rank, step)
+        comm.exchange(buf, off, own, plane, lower=lower, upper=upper, width=width)
+        return n
+
+    def check(step, lower, upper, n):
+        lo, hi = buf[off - n:off], buf[off + own:off + own + n]
+        if lower and rank > 0:
+            assert torch.equal(lo, pattern(rank - 1, step)[own - n:]), ("lower halo", step)
+        else:
+            assert bool((lo == -1.0).all()), ("lower halo must stay untouched", step)
+        if upper and rank < world - 1:
+            assert torch.equal(hi, pattern(rank + 1, step)[:n]), ("upper halo", step)
+        else:
+            assert bool((hi == -1.0).all()), ("upper halo must stay untouched", step)
+
+    nred = 0
+    for step in range(120):
+        lower, upper = [(True, True), (True, False), (False, True)][int(rng.integers(0, 3))]
+        width = int(rng.integers(1, 3))
+        n = run(step, lower, upper, width)
+        check(step, lower, upper, n)
+        if rng.random() < 0.5:
+            k = int(rng.integers(1, 17))
+            mine = torch.tensor(np.random.default_rng(1000 * step + rank).standard_normal(k), device=dev)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            op = "sum" if rng.random() < 0.7 else "max"
+            want = parts[0].clone()
+            for q in parts[1:]:
+                want = want + q if op == "sum" else torch.maximum(want, q)
+            got = comm.allreduce_(mine.clone(), op)
+            assert torch.equal(got, want), ("peer all-reduce", step, op, got, want)
+            nred += 1
+    assert comm.fast_exchanges == 120 and comm.fast_allreduces == nred
+    # a captured sequence (two-way, one-way up, one-way down) replayed between eager exchanges
+    src = pattern(rank, 0).clone()
+    comm.barrier()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        buf[off:off + own] = src
+        comm.exchange(buf, off, own, plane, lower=True, upper=True)
+        comm.exchange(buf, off, own, plane, lower=True, upper=False, width=2)
+        comm.exchange(buf, off, own, plane, lower=False, upper=True, width=2)
+    for step in range(200, 212):
+        src.copy_(pattern(rank, step))
+        buf.fill_(-1.0)
+        g.replay()
+        check(step, True, True, 2 * plane)
+        n = run(step + 50, True, True, 1)
+        check(step + 50, True, True, n)
+    comm.check_peer_timeouts()
+    if rank == 0:
+        print(f"[dist_check] peer primitives on {world} ranks: 120 + 12 x 4 one-launch halo exchanges (two-way / one-way, eager and "
+              f"graph-replayed) and {nred} one-launch all-reduces exact")
+    pmb.slab.reset()
 
 
 def filterconv_slabs(rank, world):

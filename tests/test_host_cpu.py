@@ -212,11 +212,12 @@ def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
 #define S(t) printf(#t " %zu\n", sizeof(t))
 #define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
 int main(void) {
-  S(pmb_grid); S(pmb_coef); S(pmb_bound); S(pmb_mma_vecs); S(pmb_mg_level); S(pmb_mg_desc); S(pmb_elem_op);
+  S(pmb_grid); S(pmb_coef); S(pmb_bound); S(pmb_mma_vecs); S(pmb_mg_level); S(pmb_mg_desc); S(pmb_elem_op); S(pmb_peer_halo); S(pmb_peer_reduce);
   O(pmb_coef, sqrt_den); O(pmb_bound, v); O(pmb_mma_vecs, Q); O(pmb_mg_level, A); O(pmb_mg_level, smooth_steps);
   O(pmb_mg_level, w); O(pmb_mg_desc, level); O(pmb_mg_desc, coarse_grid); O(pmb_mg_desc, coarse_inv); O(pmb_mg_desc, gen);
   O(pmb_elem_op, bcdiagval); O(pmb_elem_op, brickflags); O(pmb_elem_op, variant);
-  printf("PMB_MMA_MAXM %d\nPMB_MAX_LEVELS %d\n", PMB_MMA_MAXM, PMB_MAX_LEVELS);
+  O(pmb_peer_halo, box_hi); O(pmb_peer_halo, ctl); O(pmb_peer_halo, cap); O(pmb_peer_reduce, slots); O(pmb_peer_reduce, ctl);
+  printf("PMB_MMA_MAXM %d\nPMB_MAX_LEVELS %d\nPMB_PEER_MAX %d\nPMB_PEER_COUNT_MAX %d\n", PMB_MMA_MAXM, PMB_MAX_LEVELS, PMB_PEER_MAX, PMB_PEER_COUNT_MAX);
   return 0;
 }
 ''')
@@ -224,7 +225,8 @@ int main(void) {
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     mirrors = {"pmb_grid": _lib.Grid, "pmb_coef": _lib.Coef, "pmb_bound": _lib.Bound, "pmb_mma_vecs": _lib.MmaVecs,
-               "pmb_mg_level": _lib.MgLevel, "pmb_mg_desc": _lib.MgDesc, "pmb_elem_op": _lib.ElemOp}
+               "pmb_mg_level": _lib.MgLevel, "pmb_mg_desc": _lib.MgDesc, "pmb_elem_op": _lib.ElemOp,
+               "pmb_peer_halo": _lib.PeerHalo, "pmb_peer_reduce": _lib.PeerReduce}
     for name, cls in mirrors.items():
         assert int(got[name]) == ctypes.sizeof(cls), (name, got[name], ctypes.sizeof(cls))
     for key, val in got.items():
@@ -232,6 +234,7 @@ int main(void) {
             st, field = key.split(".")
             assert int(val) == getattr(mirrors[st], field).offset, (key, val)
     assert int(got["PMB_MMA_MAXM"]) == _lib.MMA_MAXM and int(got["PMB_MAX_LEVELS"]) == _lib.MAX_LEVELS
+    assert int(got["PMB_PEER_MAX"]) == _lib.PEER_MAX and int(got["PMB_PEER_COUNT_MAX"]) == _lib.PEER_COUNT_MAX
 
 
 def test_direct_coarse_operator_tables_vs_oracle():
