@@ -28,6 +28,8 @@
  *                        pymoto/common/mma.py:129-140,178-217 (asymptote offsets; low/upp/alfa/beta/P/Q, rhs sums)
  *   pmb_mma_residual / pmb_mma_newton_sums / pmb_mma_newton_dir / pmb_mma_linesearch
  *                        pymoto/common/mma.py:313-336,349-392,401-423,428-462 (n-sized parts of subsolv)
+ *   pmb_mma_gcmma_rho / pmb_mma_gcmma_estimate
+ *                        pymoto/common/mma.py:151,236-239 (GCMMA: initial rho sums; approximation values and dk)
  *   pmb_pack_f32         pymoto/common/domain.py:541-548,579-583 (Float32 VTI payload, 2 -> 3 component padding)
  *   pmb_vcycle / pmb_pcg_solve
  *                        pymoto/solvers/iterative.py:222-256,340-403 (one V-cycle; the whole PCG solve driven from C)
@@ -337,6 +339,13 @@ int pmb_mma_newton_dir(long long n, int m, const pmb_mma_vecs* v, const double* 
                        double* ws, void* stream);
 int pmb_mma_linesearch(long long n, int m, const pmb_mma_vecs* v, const double* lam, double steg, double epsi, double* out,
                        double* ws, void* stream);
+/* GCMMA (mma.py:104-160, 232-242; the inner loop and the rho update stay with the caller on the host).  gcmma_rho:
+ * out[i] = sum_j (xmax_j - xmin_j) |dg_i[j]|, i = 0..m (:151; rho = 0.1 / n * out; the subproblem is then set up with version 2007 and
+ * max(rho_i, 1e-6), which is the reference's GCMMA P / Q formula, :213-216).  gcmma_estimate, after the subproblem solve:
+ * out[i] = sum_j P_ij / (upp_j - x_j) + Q_ij / (x_j - low_j), i = 0..m (gest = out - rhs, :236) and out[m+1] = dk (:239). */
+int pmb_mma_gcmma_rho(long long n, int m, const double* const* dg, pmb_bound xmin, pmb_bound xmax, double* out, double* ws, void* stream);
+int pmb_mma_gcmma_estimate(long long n, int m, const pmb_mma_vecs* v, const double* xval, pmb_bound xmin, pmb_bound xmax, double* out,
+                           double* ws, void* stream);
 
 /* ---- whole linear solve driven from C (pymoto/solvers/iterative.py:340-403 CG.solve with :222-256 GeometricMultigrid.solve
  * as preconditioner): the same kernel launches as the entry points above, issued in the reference's order, the host

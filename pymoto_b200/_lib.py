@@ -160,6 +160,8 @@ SIGNATURES = {
     "pmb_mma_newton_sums": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _P, _P, _P]),
     "pmb_mma_newton_dir": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), C.POINTER(C.c_double), _D, _P, _P, _P]),
     "pmb_mma_linesearch": (_I, [_LL, _I, C.POINTER(MmaVecs), C.POINTER(C.c_double), _D, _D, _P, _P, _P]),
+    "pmb_mma_gcmma_rho": (_I, [_LL, _I, C.POINTER(C.c_void_p), Bound, Bound, _P, _P, _P]),
+    "pmb_mma_gcmma_estimate": (_I, [_LL, _I, C.POINTER(MmaVecs), _P, Bound, Bound, _P, _P, _P]),
     "pmb_probe_fp64_out_doubles": (_LL, []),
     "pmb_probe_fp64": (_I, [_I, _I, _P, C.POINTER(C.c_double), _P]),
     "pmb_pack_f32": (_I, [_LL, _I, _I, _P, _P, _P]),

@@ -137,8 +137,19 @@ except Exception:  # ModuleNotFoundError (pymoto or its matplotlib import)
         active = []
 
         def __init__(self, *mods, print_timing=False):
-            self.mods = list(mods)
+            self.mods = []
+            for m in mods:  # modules or lists of modules (core_objects.py:775-780)
+                self.mods.extend(_as_list(m))
             self.print_timing = print_timing
+
+        def __len__(self):
+            return len(self.mods)
+
+        def __iter__(self):
+            return iter(self.mods)
+
+        def __getitem__(self, i):
+            return self.mods[i]
 
         def __enter__(self):
             Network.active.append(self)
@@ -166,3 +177,31 @@ except Exception:  # ModuleNotFoundError (pymoto or its matplotlib import)
         def reset(self):
             for m in reversed(self.mods):
                 m.reset()
+
+        @staticmethod
+        def _signal_set(sigs):
+            return {id(s) for s in _as_list(sigs) if _is_signal(s)}
+
+        def get_input_cone(self, fromsig=None, frommod=None):
+            """Modules that depend on ``fromsig`` (or follow ``frommod``), in evaluation order (core_objects.py:913-928)."""
+            touched, frommod = self._signal_set(fromsig), {id(m) for m in _as_list(frommod)}
+            if not touched and not frommod:
+                return self
+            cone = Network(print_timing=self.print_timing)
+            for m in self.mods:
+                if id(m) in frommod or (self._signal_set(m.sig_in) & touched):
+                    touched |= self._signal_set(m.sig_out)
+                    cone.append(m)
+            return cone
+
+        def get_output_cone(self, tosig=None, tomod=None):
+            """Modules ``tosig`` (or ``tomod``) depend on, in evaluation order (core_objects.py:930-945)."""
+            dependent, tomod = self._signal_set(tosig), {id(m) for m in _as_list(tomod)}
+            if not dependent and not tomod:
+                return self
+            cone = []
+            for m in reversed(self.mods):
+                if id(m) in tomod or (self._signal_set(m.sig_out) & dependent):
+                    dependent |= self._signal_set(m.sig_in)
+                    cone.append(m)
+            return Network(list(reversed(cone)), print_timing=self.print_timing)

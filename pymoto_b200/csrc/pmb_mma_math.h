@@ -123,3 +123,17 @@ MMA_HD void mma_dir_pt(const MmaVar& v, const MmaSmall& lam, const MmaSmall& dla
   cand[2] = -dx / (v.x - v.alfa);
   cand[3] = dx / (v.beta - v.x);
 }
+
+// ---- GCMMA (mma.py:104-160, 232-242)
+// initial conservativeness rho_i = 0.1/n sum_j dx_j |dg_ij| (:151): the term of one variable and one response
+MMA_HD double mma_rho_term(double dgij, double xmin, double xmax) { return (xmax - xmin) * fabs(dgij); }
+
+// value of the convex approximations at the subproblem solution (:236, before "- rhs"): est_i += P_i/(upp-x) + Q_i/(x-low) for
+// i = 0..M, and the variable's term of the normalised step measure dk (:239)
+template <int M>
+MMA_HD double mma_estimate_pt(const MmaVar& v, double xval, double xmin, double xmax, double* est) {
+  const double ux1 = v.upp - v.x, xl1 = v.x - v.low;
+  for (int i = 0; i <= M; ++i) est[i] += v.P[i] / ux1 + v.Q[i] / xl1;
+  const double dxm = v.x - xval;
+  return (v.upp - v.low) * (dxm * dxm) / (ux1 * xl1 * (xmax - xmin));
+}

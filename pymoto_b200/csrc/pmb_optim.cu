@@ -163,7 +163,7 @@ extern "C" int pmb_mma_setup(long long n, int m, const double* xval, const doubl
                              double* out, double* ws, void* stream) {
   if (check_vecs(v, "pmb_mma_setup")) return 1;
   PMB_REQUIRE(n > 0 && xval && dg && offset && rho && out && ws, "pmb_mma_setup: invalid argument");
-  PMB_REQUIRE(version == 1987 || version == 2007, "pmb_mma_setup: version must be 1987 or 2007 (GCMMA is not built)");
+  PMB_REQUIRE(version == 1987 || version == 2007, "pmb_mma_setup: version must be 1987 or 2007 (GCMMA: 2007 with per-response rho >= 1e-6)");
   PMB_REQUIRE(m >= 1 && m <= PMB_MMA_MAXM, "pmb_mma_setup: m=%d not in 1..%d", m, PMB_MMA_MAXM);
   MmaRows rows;
   for (int i = 0; i <= PMB_MMA_MAXM; ++i) rows.r[i] = i <= m ? dg[i] : nullptr;
@@ -299,6 +299,61 @@ extern "C" int pmb_mma_linesearch(long long n, int m, const pmb_mma_vecs* v, con
   const MmaSmall l = small_from(lam, m);
   MMA_DISPATCH(m, (mma_linesearch_kernel<M><<<opt_blocks(n), OPT_THREADS, 0, (cudaStream_t)stream>>>(n, *v, l, steg, epsi, out, ws)));
   PMB_CHECK_LAUNCH("pmb_mma_linesearch");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- GCMMA passes
+// out[i] = sum_j (xmax_j - xmin_j) |dg_i[j]|, i = 0..m   (mma.py:151; the caller scales by 0.1 / n)
+template <int M>
+__global__ void __launch_bounds__(OPT_THREADS) mma_gcmma_rho_kernel(long long n, MmaRows dg, pmb_bound xmin, pmb_bound xmax, double* out,
+                                                                    double* ws) {
+  double s[M + 1], mx[1] = {0.0};
+#pragma unroll
+  for (int i = 0; i <= M; ++i) s[i] = 0.0;
+  const long long stride = (long long)gridDim.x * OPT_THREADS;
+  for (long long j = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; j < n; j += stride) {
+    const double lo = bound_at(xmin, j), hi = bound_at(xmax, j);
+#pragma unroll
+    for (int i = 0; i <= M; ++i) s[i] += mma_rho_term(dg.r[i][j], lo, hi);
+  }
+  opt_reduce<M + 1, 0>(s, mx, ws, out);
+}
+
+extern "C" int pmb_mma_gcmma_rho(long long n, int m, const double* const* dg, pmb_bound xmin, pmb_bound xmax, double* out, double* ws,
+                                 void* stream) {
+  PMB_REQUIRE(n > 0 && dg && out && ws, "pmb_mma_gcmma_rho: invalid argument");
+  PMB_REQUIRE(m >= 1 && m <= PMB_MMA_MAXM, "pmb_mma_gcmma_rho: m=%d not in 1..%d", m, PMB_MMA_MAXM);
+  MmaRows rows;
+  for (int i = 0; i <= PMB_MMA_MAXM; ++i) rows.r[i] = i <= m ? dg[i] : nullptr;
+  for (int i = 0; i <= m; ++i) PMB_REQUIRE(rows.r[i], "pmb_mma_gcmma_rho: NULL sensitivity row %d", i);
+  MMA_DISPATCH(m, (mma_gcmma_rho_kernel<M><<<opt_blocks(n), OPT_THREADS, 0, (cudaStream_t)stream>>>(n, rows, xmin, xmax, out, ws)));
+  PMB_CHECK_LAUNCH("pmb_mma_gcmma_rho");
+  return 0;
+}
+
+// out[0..m] = sum_j P_ij/(upp_j - x_j) + Q_ij/(x_j - low_j) at the subproblem solution x (mma.py:236 without "- rhs"),
+// out[m+1] = dk = sum_j (upp-low)(x-xval)^2 / ((upp-x)(x-low)(xmax-xmin))   (:239)
+template <int M>
+__global__ void __launch_bounds__(OPT_THREADS) mma_gcmma_estimate_kernel(long long n, pmb_mma_vecs a, const double* __restrict__ xval,
+                                                                         pmb_bound xmin, pmb_bound xmax, double* out, double* ws) {
+  double s[M + 2], mx[1] = {0.0};
+#pragma unroll
+  for (int i = 0; i < M + 2; ++i) s[i] = 0.0;
+  const long long stride = (long long)gridDim.x * OPT_THREADS;
+  for (long long j = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; j < n; j += stride) {
+    MmaVar v;
+    load_var<M>(a, n, j, v);
+    s[M + 1] += mma_estimate_pt<M>(v, xval[j], bound_at(xmin, j), bound_at(xmax, j), s);
+  }
+  opt_reduce<M + 2, 0>(s, mx, ws, out);
+}
+
+extern "C" int pmb_mma_gcmma_estimate(long long n, int m, const pmb_mma_vecs* v, const double* xval, pmb_bound xmin, pmb_bound xmax,
+                                      double* out, double* ws, void* stream) {
+  if (check_vecs(v, "pmb_mma_gcmma_estimate")) return 1;
+  PMB_REQUIRE(n > 0 && xval && out && ws, "pmb_mma_gcmma_estimate: invalid argument");
+  MMA_DISPATCH(m, (mma_gcmma_estimate_kernel<M><<<opt_blocks(n), OPT_THREADS, 0, (cudaStream_t)stream>>>(n, *v, xval, xmin, xmax, out, ws)));
+  PMB_CHECK_LAUNCH("pmb_mma_gcmma_estimate");
   return 0;
 }
 

@@ -36,14 +36,39 @@ def _gnorm(v):
     return float(torch.sqrt(_allreduce((v * v).sum().reshape(1)))[0])
 
 
+def select_network(function, variables, responses, slice_network=False):
+    """The Network an optimiser evaluates (pymoto/common/optimizers.py:52-72): the given one, else the outermost active
+    Network; with ``slice_network`` only the modules that connect the variable Signals to the response Signals, after
+    running whatever the variables themselves depend on when they have no state yet."""
+    from .core import Network
+
+    if function is None:
+        if not Network.active:
+            raise RuntimeError("No Network given and no active Network to take the optimisation problem from")
+        function = Network.active[0]
+    if not slice_network:
+        return function
+    subfn = function.get_output_cone(responses).get_input_cone(variables)
+    if len(subfn) == 0:
+        raise RuntimeError(f"Could not find a network that uses the provided input signals {variables} and produces the requested "
+                           f"output signals {responses}")
+    for s in variables:
+        if s.state is None:
+            function.get_output_cone(tosig=s).response()
+        if s.state is None:
+            raise RuntimeError(f"Input signal {s} has no state.")
+    return subfn
+
+
 class OC:
-    def __init__(self, variables, response, function, move=0.1, xmin=0.0, xmax=1.0, verbosity: int = 2, l1init: float = 0.0,
+    def __init__(self, variables, response, function=None, slice_network=False, move=0.1, xmin=0.0, xmax=1.0, verbosity: int = 2, l1init: float = 0.0,
                  l2init: float = 100000.0, l1l2tol: float = 1e-4, maxvol: float = None):
         if isinstance(variables, (list, tuple)):
             if len(variables) != 1:
                 raise NotImplementedError("pymoto_b200.OC handles one design-variable Signal")
             variables = variables[0]
-        self.variable, self.response, self.function = variables, response, function
+        self.variable, self.response = variables, response
+        self.function = select_network(function, [variables], [response], slice_network)
         if any(np.size(v) != 1 for v in (move, xmin, xmax)):
             raise NotImplementedError("pymoto_b200.OC takes scalar move / xmin / xmax (vector bounds: use pymoto_b200.MMA)")
         self.move, self.xmin, self.xmax = (float(np.asarray(v).reshape(-1)[0]) for v in (move, xmin, xmax))
@@ -218,6 +243,24 @@ class MmaDeviceOps:
                   dv.ptr(self.out), dv.ptr(self.ws), dv.stream())
         return self._resid_out()
 
+    def rho_sums(self, dg_rows, xmin, xmax):
+        """sum_j (xmax_j - xmin_j) |dg_i[j]| for the m+1 rows (GCMMA, mma.py:151), global over slabs."""
+        rows = (self._C.c_void_p * (self.m + 1))(*[r.data_ptr() for r in dg_rows])
+        self._keep = (dg_rows, xmin, xmax)
+        _lib.call("pmb_mma_gcmma_rho", self.n, self.m, rows, self._bound(xmin), self._bound(xmax), dv.ptr(self.out), dv.ptr(self.ws),
+                  dv.stream())
+        self._reduce(self.m + 1)
+        return self.out[: self.m + 1].cpu().numpy()
+
+    def estimate(self, xval, xmin, xmax):
+        """Approximation values at the subproblem solution (before ``- rhs``) and dk (GCMMA, mma.py:236-239)."""
+        self._keep = (xval, xmin, xmax)
+        _lib.call("pmb_mma_gcmma_estimate", self.n, self.m, self._C.byref(self.vecs), dv.ptr(xval), self._bound(xmin), self._bound(xmax),
+                  dv.ptr(self.out), dv.ptr(self.ws), dv.stream())
+        self._reduce(self.m + 2)
+        o = self.out[: self.m + 2].cpu().numpy()
+        return o[: self.m + 1].copy(), float(o[self.m + 1])
+
 
 def mma_subsolv(ops, m, epsimin, a0, a, b, c, d, maxittt=400):
     """Primal-dual Newton solution of the MMA subproblem, pymoto/common/mma.py:246-474, with every n-sized expression
@@ -286,21 +329,78 @@ def mma_subsolv(ops, m, epsimin, a0, a, b, c, d, maxittt=400):
     return y, z, lam, mu, zet, s, newton_its
 
 
+def mma_subproblem(ops, x, g, dg, offset, xmin, xmax, move, opt, estimate=False):
+    """Set up and solve one MMA subproblem around ``x`` (mmasub, mma.py:170-244) with the asymptote offsets as they are.
+    ``opt["rho"]``: one value (MMA2007) or one per response (GCMMA; a single response's value also serves the dummy constraint
+    of an unconstrained problem, as the reference's broadcast does).  The new design is left in ``ops.x``.  With ``estimate``
+    the values of the convex approximations at the new design and the step measure are returned too (``gest``, ``dk``,
+    :236-239).  Returns (lam, Newton iterations, gest, dk)."""
+    m, n = ops.m, ops.n
+    unconstrained = g.size == 1
+    if unconstrained:  # dummy constraint with zero sensitivities (mma.py:172-175)
+        g = np.hstack((g, -1.0))
+        dg = dg + [ops.zeros(n)]
+    rho = np.atleast_1d(np.asarray(opt["rho"], dtype=float))
+    if rho.size == 1:
+        rho = np.full(m + 1, rho[0])
+    sums = ops.setup(x, dg, offset, xmin, xmax, move, opt["albefa"], list(rho), opt["version"])
+    rhs = sums - g
+    epsimin_scaled = opt["epsimin"] * np.sqrt(m + getattr(ops, "n_global", n))
+    y, z, lam, mu, zet, s, its = mma_subsolv(ops, m, epsimin_scaled, opt["a0"], opt["a"], rhs[1:], opt["c"], opt["d"])
+    gest = dk = None
+    if estimate:
+        est, dk = ops.estimate(x, xmin, xmax)
+        gest = est - rhs
+        if unconstrained:
+            gest = gest[:1]
+    return lam, its, gest, dk
+
+
 def mma_design_update(ops, x, g, dg, offset, xold1, xold2, xmin, xmax, move, opt):
     """One MMA design update (mma.py:101-244, non-GCMMA branch): asymptote offsets from the last two designs, subproblem
     set-up, primal-dual solve.  ``ops`` owns the n-sized state (the new design is left in ``ops.x``); ``offset`` is updated
     in place; ``g`` (host, one value per response) and ``dg`` (list of rows) are not modified.  Returns (lam, Newton its)."""
-    m, n = ops.m, ops.n
     if xold1 is not None and xold2 is not None:
         ops.asymptotes(x, xold1, xold2, offset, opt["asyincr"], opt["asydecr"], opt["asybound"])
-    if g.size == 1:  # unconstrained: dummy constraint with zero sensitivities (mma.py:172-175)
-        g = np.hstack((g, -1.0))
-        dg = dg + [ops.zeros(n)]
-    sums = ops.setup(x, dg, offset, xmin, xmax, move, opt["albefa"], [opt["rho"]] * (m + 1), opt["version"])
-    rhs = sums - g
-    epsimin_scaled = opt["epsimin"] * np.sqrt(m + getattr(ops, "n_global", n))
-    y, z, lam, mu, zet, s, its = mma_subsolv(ops, m, epsimin_scaled, opt["a0"], opt["a"], rhs[1:], opt["c"], opt["d"])
+    lam, its, _, _ = mma_subproblem(ops, x, g, dg, offset, xmin, xmax, move, opt)
     return lam, its
+
+
+def gcmma_rho_update(rho, g, gest, dk):
+    """Raise the conservativeness of the responses whose approximation under-estimated the new value (mma.py:152-154)."""
+    delta = (g - gest) / dk
+    upd = delta > 0
+    rho = rho.copy()
+    rho[upd] = np.minimum(1.1 * (rho + delta), 10 * rho)[upd]
+    return rho
+
+
+def gcmma_design_update(ops, x, gk, dg, offset, xmin, xmax, move, opt, evaluate, maxit=20, verbosity=0):
+    """The inner iterations of one GCMMA design update (mma.py:142-160) around the outer design ``x`` with responses ``gk``
+    and sensitivity rows ``dg``; the asymptote offsets are updated by the caller beforehand.  ``evaluate(xcand)`` returns
+    the responses at a candidate design (``xcand`` is ``ops.x``: copy it if it is kept).  Each pass solves the subproblem
+    with P / Q of MMA2007 and ``max(rho_i, 1e-6)`` per response; the loop ends when every approximation was conservative
+    (``gest >= g``) at the last candidate, which then is the new design left in ``ops.x``.
+    Returns a dict: lam, newton_its, g (at the last evaluated design), rho, gest, dk, inner (subproblems solved)."""
+    n_global = getattr(ops, "n_global", ops.n)
+    rows = list(dg) if len(dg) > 1 else list(dg) + [ops.zeros(ops.n)]
+    rho = 0.1 / n_global * ops.rho_sums(rows, xmin, xmax)[: len(dg)]
+    g, gest, dk, lam, newton_its, inner = gk, None, None, None, 0, 0
+    for gcmmait in range(maxit):
+        if gcmmait > 0:
+            g = np.asarray(evaluate(ops.x), dtype=float)
+            if np.all(gest >= g):
+                if verbosity >= 3:
+                    print(f"  || GCMMA converged in {gcmmait} inner iterations")
+                break
+            rho = gcmma_rho_update(rho, g, gest, dk)
+            if verbosity >= 3:
+                print(f"  || GCMMA It. {gcmmait}, g = {g}, gest = {gest}, rho={rho}")
+        lam, its, gest, dk = mma_subproblem(ops, x, gk, list(dg), offset, xmin, xmax, move, dict(opt, rho=np.maximum(rho, 1e-6)),
+                                            estimate=True)
+        newton_its += its
+        inner += 1
+    return dict(lam=lam, newton_its=newton_its, g=g, rho=rho, gest=gest, dk=dk, inner=inner)
 
 
 class MMA:
@@ -310,16 +410,15 @@ class MMA:
     Same constructor and keyword options as the reference (``move, xmin, xmax, mmaversion ("MMA1987" | "MMA2007"), a0,
     epsimin, cCoef, albefa, asyinit, asyincr, asydecr, asybound, a, c``); bounds and move limits may be scalars, one value
     per variable Signal, or full vectors.  Variable states may be numpy arrays or CUDA tensors (each Signal keeps its
-    kind).  Not built: ``mmaversion="GCMMA"`` and ``slice_network=True``."""
+    kind).  ``mmaversion="GCMMA"`` runs the globally convergent inner loop (``gcmma_maxit``), ``slice_network=True`` evaluates
+    only the modules between the variables and the responses."""
 
     def __init__(self, variables, responses, function, slice_network=False, move=0.1, xmin=0.0, xmax=1.0, verbosity=2,
                  mmaversion="MMA2007", **kwargs):
         dv.require_cuda()
-        if slice_network:
-            raise NotImplementedError("pymoto_b200.MMA evaluates the whole Network (slice_network=False)")
         self.variables = list(variables) if isinstance(variables, (list, tuple)) else [variables]
         self.responses = list(responses) if isinstance(responses, (list, tuple)) else [responses]
-        self.function, self.verbosity = function, verbosity
+        self.function, self.verbosity = select_network(function, self.variables, self.responses, slice_network), verbosity
         self._host = [not dv.is_device(s.state) for s in self.variables]
         sizes = [int(np.size(s.state)) if h else int(s.state.numel()) for s, h in zip(self.variables, self._host)]
         self._cumlens = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
@@ -330,12 +429,13 @@ class MMA:
         self.move = self._parse_bound(move, "move")
         self.iter = 0
         version = str(mmaversion).lower()
-        if "gcmma" in version:
-            raise NotImplementedError("pymoto_b200.MMA: GCMMA is not built (use MMA1987 or MMA2007)")
+        self._gcmma = False
         if "1987" in version:
             self._version = 1987
         elif "2007" in version:
             self._version = 2007
+        elif "gcmma" in version:  # GCMMA's P / Q are MMA2007's with rho_i = max(rho_i, 1e-6) per response (mma.py:213-216)
+            self._version, self._gcmma = 2007, True
         else:
             raise ValueError('Only "MMA1987", "MMA2007", or "GCMMA" are valid options')
         self.mmaversion = mmaversion
@@ -347,6 +447,9 @@ class MMA:
         self.asyincr = kwargs.get("asyincr", 1.2)
         self.asydecr = kwargs.get("asydecr", 0.7)
         self.asybound = kwargs.get("asybound", 10.0)
+        self.gcmma_maxit = kwargs.get("gcmma_maxit", 20)
+        self.gest = self.dk = None
+        self.gcmma_inner_iterations = 0
         self.dx = self.xmax - self.xmin  # float or CUDA tensor
         self.xold1 = self.xold2 = None
         self.offset = torch.full((self.n,), float(self.asyinit), dtype=torch.float64, device=dv.require_cuda())
@@ -429,7 +532,13 @@ class MMA:
             self.function.reset()
         return rows
 
+    def _evaluate_candidate(self, xcand):
+        self.x = xcand.clone()
+        return self.calculate_g()
+
     def step(self, x=None, g=None, dg=None):
+        """One design update (mma.py:96-168).  MMA: one subproblem.  GCMMA: inner iterations at the asymptotes and sensitivities
+        of the outer design ``x``, each re-evaluating the responses at the candidate (the variable Signals are left there)."""
         if x is None:
             x = self.x
         else:
@@ -437,12 +546,21 @@ class MMA:
         if g is None:
             g = self.calculate_g()
         if dg is None:
-            dg = self.calculate_dg()
-        self.rho = 1e-5
-        self.lam, self.newton_iterations = mma_design_update(
-            self.ops, x, np.asarray(g, dtype=float), list(dg), self.offset, self.xold1, self.xold2, self.xmin, self.xmax, self.move,
-            dict(version=self._version, albefa=self.albefa, asyincr=self.asyincr, asydecr=self.asydecr, asybound=self.asybound,
-                 a0=self.a0, a=self.a, c=self.c, d=self.d, epsimin=self.epsimin, rho=self.rho))
+            dg = self.calculate_dg()  # once per outer iteration
+        g = np.asarray(g, dtype=float)
+        opt = dict(version=self._version, albefa=self.albefa, asyincr=self.asyincr, asydecr=self.asydecr, asybound=self.asybound,
+                   a0=self.a0, a=self.a, c=self.c, d=self.d, epsimin=self.epsimin)
+        if self.xold1 is not None and self.xold2 is not None:
+            self.ops.asymptotes(x, self.xold1, self.xold2, self.offset, self.asyincr, self.asydecr, self.asybound)
+        if self._gcmma:
+            r = gcmma_design_update(self.ops, x, g, list(dg), self.offset, self.xmin, self.xmax, self.move, opt, self._evaluate_candidate,
+                                    self.gcmma_maxit, self.verbosity)
+            self.lam, self.newton_iterations, g = r["lam"], r["newton_its"], r["g"]
+            self.rho, self.gest, self.dk, self.gcmma_inner_iterations = r["rho"], r["gest"], r["dk"], r["inner"]
+        else:
+            self.rho = opt["rho"] = 1e-5
+            self.lam, self.newton_iterations, _, _ = mma_subproblem(self.ops, x, g, list(dg), self.offset, self.xmin, self.xmax,
+                                                                    self.move, opt)
         xnew = self.ops.x.clone()
         self.xold2, self.xold1 = self.xold1, x.clone()
         return xnew, g, dg

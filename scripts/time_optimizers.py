@@ -49,7 +49,7 @@ def main():
         xold2, xold1 = xold1, x.clone()
         x = ops.x.clone()
     # ---- OC
-    oc = pmb.OC(pmb.Signal("x", state=x), pmb.Signal("c", state=1.0), None, verbosity=0)
+    oc = pmb.OC(pmb.Signal("x", state=x), pmb.Signal("c", state=1.0), pmb.Network(), verbosity=0)
     oc_ms = []
     for k in range(3):
         torch.cuda.synchronize()

@@ -1,11 +1,13 @@
 """Golden fixtures for the optimiser rows from the UNMODIFIED reference (pyMOTO at /root/reference).
 
-    python tests/golden/make_golden_opt.py [oc] [mma] [subsolv] [vti]
+    python tests/golden/make_golden_opt.py [oc] [mma] [subsolv] [gcmma] [vti]
 
   ref_oc_mbb100x50.npz   10 OC iterations of the 2-D MBB 100x50 problem (BASELINE configs[0]; pym.OC.step)
   ref_mma_mbb60x30.npz   8 MMA2007 iterations, 2-D MBB 60x30, compliance objective (Scaling 100) + volume constraint (Scaling 10)
   ref_mma_hex16x8x8.npz  6 MMA2007 iterations, 3-D cantilever 16x8x8, same responses
   ref_mma_subsolv.npz    single subproblems (pym.MMA.mmasub on seeded data): m = 1, 2, unconstrained, MMA1987, vector bounds
+  ref_gcmma.npz          6 GCMMA outer iterations (pym.MMA(mmaversion="GCMMA").step through a Network) of two seeded analytic problems:
+                         designs, responses, rho, number of response evaluations per outer iteration
   ref_vti.npz            bytes of VoxelDomain.write_to_vti files (2-D with vector padding, 3-D, block vectors)
 """
 import os
@@ -18,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from _refimport import import_reference  # noqa: E402
-from make_golden_opt_inputs import SUBSOLV_CASES, subsolv_inputs, vti_inputs  # noqa: E402
+from make_golden_opt_inputs import GCMMA_CASES, SUBSOLV_CASES, gcmma_problem, subsolv_inputs, vti_inputs  # noqa: E402
 
 pym = import_reference()
 assert pym is not None, "reference not found at /root/reference"
@@ -103,6 +105,40 @@ def subsolv_case():
     np.savez_compressed(os.path.join(HERE, "ref_mma_subsolv.npz"), **out)
 
 
+def gcmma_case(iters=6):
+    out = {}
+    for name in GCMMA_CASES:
+        n, x0, responses = gcmma_problem(name)
+        nresp = GCMMA_CASES[name][1]
+        evals = [0]
+
+        class Analytic(pym.Module):
+            def __call__(self, x):
+                evals[0] += 1
+                return tuple(responses(x)[0])
+
+            def _sensitivity(self, *dg):
+                J = responses(self.sig_in[0].state)[1]
+                return sum(d * J[i] for i, d in enumerate(dg) if d is not None)
+
+        sx = pym.Signal("x", state=x0.copy())
+        fn = pym.Network()
+        with fn:
+            resp = Analytic()(sx)
+        resp = list(resp) if isinstance(resp, (tuple, list)) else [resp]
+        mma = pym.MMA(sx, resp, fn, verbosity=0, mmaversion="GCMMA")
+        x, xs, gs, rhos, nev = sx.state.copy(), [], [], [], []
+        for _ in range(iters):
+            e0 = evals[0]
+            xnew, g, dg = mma.step(x)
+            xs.append(xnew.copy()); gs.append(np.array(g, dtype=float)); rhos.append(np.array(mma.rho, dtype=float)); nev.append(evals[0] - e0)
+            x = xnew.copy()
+        print("gcmma", name, "evaluations per outer iteration", nev, "g", [tuple(np.round(g, 5)) for g in gs])
+        out[name + "_x"], out[name + "_g"], out[name + "_rho"], out[name + "_nev"] = np.array(xs), np.array(gs), np.array(rhos), np.array(nev)
+        out[name + "_offset"] = mma.offset
+    np.savez_compressed(os.path.join(HERE, "ref_gcmma.npz"), **out)
+
+
 def vti_case():
     out = {}
     for name in ("2d", "3d", "block"):
@@ -117,7 +153,7 @@ def vti_case():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["oc", "mma", "subsolv", "vti"]
+    what = sys.argv[1:] or ["oc", "mma", "subsolv", "gcmma", "vti"]
     if "oc" in what:
         oc_case()
     if "mma" in what:
@@ -125,5 +161,7 @@ if __name__ == "__main__":
         mma_history("mma_hex16x8x8", *cantilever3d(16, 8, 8), iters=6)
     if "subsolv" in what:
         subsolv_case()
+    if "gcmma" in what:
+        gcmma_case()
     if "vti" in what:
         vti_case()

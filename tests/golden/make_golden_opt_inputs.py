@@ -31,6 +31,34 @@ def subsolv_inputs(name):
     return dict(n=n, nresp=nresp, version=version, x=x, xold1=xold1, xold2=xold2, g=g, dg=dg, xmin=xmin, xmax=xmax, move=move)
 
 
+GCMMA_CASES = {
+    # name: (n, number of responses)
+    "gcmma_m2": (150, 3),
+    "gcmma_unconstrained": (90, 1),
+}
+
+
+def gcmma_problem(name):
+    """A seeded analytic, deliberately non-convex problem (the oscillating term makes MMA approximations non-conservative, so
+    GCMMA's inner iterations trigger): returns (n, x0, responses(x) -> (g[nresp], dg[nresp, n]))."""
+    n, nresp = GCMMA_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    w, v, u = 1.0 + rng.random(n), rng.standard_normal(n), 0.5 + rng.random(n)
+    x0 = np.full(n, 0.45)
+
+    def responses(x):
+        g = [np.sum(w / (x + 0.05)) / n + 2.0 * np.sum(v * np.sin(9.0 * x)) / n]
+        dg = [-w / (x + 0.05) ** 2 / n + 18.0 * v * np.cos(9.0 * x) / n]
+        if nresp > 1:
+            g.append(np.sum(x) / n - 0.4)
+            dg.append(np.full(n, 1.0 / n))
+        if nresp > 2:
+            g.append(np.sum(u * (x - 0.3) ** 2 * np.cos(5.0 * x)) / n - 0.02)
+            dg.append(u * (2.0 * (x - 0.3) * np.cos(5.0 * x) - 5.0 * (x - 0.3) ** 2 * np.sin(5.0 * x)) / n)
+        return np.array(g), np.vstack(dg)
+
+    return n, x0, responses
+
 
 def vti_inputs(name):
     rng = np.random.default_rng(len(name))

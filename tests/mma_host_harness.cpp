@@ -110,6 +110,23 @@ static void ls_t(long long n, HVecs a, const double* lam, double steg, double ep
   out[M + 1] = mx;
 }
 
+template <int M>
+static void rho_t(long long n, const double* const* dg, HBound xmin, HBound xmax, double* out) {
+  for (int i = 0; i <= M; ++i) out[i] = 0.0;
+  for (long long j = 0; j < n; ++j)
+    for (int i = 0; i <= M; ++i) out[i] += mma_rho_term(dg[i][j], bat(xmin, j), bat(xmax, j));
+}
+template <int M>
+static void est_t(long long n, HVecs a, const double* xval, HBound xmin, HBound xmax, double* out) {
+  double s[M + 2] = {0.0};
+  for (long long j = 0; j < n; ++j) {
+    MmaVar v;
+    load<M>(a, n, j, v);
+    s[M + 1] += mma_estimate_pt<M>(v, xval[j], bat(xmin, j), bat(xmax, j), s);
+  }
+  for (int i = 0; i < M + 2; ++i) out[i] = s[i];
+}
+
 #define DISPATCH(m, CALL) \
   switch (m) { case 1: { constexpr int M = 1; CALL; } break; case 2: { constexpr int M = 2; CALL; } break; \
                case 3: { constexpr int M = 3; CALL; } break; default: return 1; }
@@ -135,6 +152,14 @@ int hmma_newton_sums(long long n, int m, const HVecs* v, const double* lam, doub
 }
 int hmma_newton_dir(long long n, int m, const HVecs* v, const double* lam, const double* dlam, double epsi, double* out) {
   DISPATCH(m, (dir_t<M>(n, *v, lam, dlam, epsi, out)));
+  return 0;
+}
+int hmma_gcmma_rho(long long n, int m, const double* const* dg, HBound xmin, HBound xmax, double* out) {
+  DISPATCH(m, (rho_t<M>(n, dg, xmin, xmax, out)));
+  return 0;
+}
+int hmma_gcmma_estimate(long long n, int m, const HVecs* v, const double* xval, HBound xmin, HBound xmax, double* out) {
+  DISPATCH(m, (est_t<M>(n, *v, xval, xmin, xmax, out)));
   return 0;
 }
 int hmma_linesearch(long long n, int m, const HVecs* v, const double* lam, double steg, double epsi, double* out) {

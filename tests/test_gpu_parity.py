@@ -1142,8 +1142,6 @@ def test_mma_design_loop_vs_reference_history(pmb, case, host):
     sx2, resp2, fn2 = _mma_chain(pmb, dom, bc, f, host)
     m2 = pmb.minimize_mma(sx2, resp2, function=fn2, maxit=2, verbosity=0)
     assert m2.iter <= 2
-    with pytest.raises(NotImplementedError):
-        pmb.MMA(sx2, resp2, fn2, mmaversion="GCMMA")
 
 
 # ------------------------------------------------------------------------------------------------ VTI output of device fields (f4)

@@ -97,6 +97,16 @@ class HostOps:
                                         self._p(self.out)) == 0
         return self.out[1:5].copy()
 
+    def rho_sums(self, dg_rows, xmin, xmax):
+        rows = (C.c_void_p * (self.m + 1))(*[r.ctypes.data for r in dg_rows])
+        assert self.lib.hmma_gcmma_rho(C.c_longlong(self.n), self.m, rows, self._b(xmin), self._b(xmax), self._p(self.out)) == 0
+        return self.out[: self.m + 1].copy()
+
+    def estimate(self, xval, xmin, xmax):
+        assert self.lib.hmma_gcmma_estimate(C.c_longlong(self.n), self.m, C.byref(self.vecs), self._p(xval), self._b(xmin), self._b(xmax),
+                                            self._p(self.out)) == 0
+        return self.out[: self.m + 1].copy(), float(self.out[self.m + 1])
+
     def linesearch(self, lam, steg, epsi):
         assert self.lib.hmma_linesearch(C.c_longlong(self.n), self.m, C.byref(self.vecs), self._h(lam), C.c_double(steg), C.c_double(epsi),
                                         self._p(self.out)) == 0
@@ -165,6 +175,98 @@ def test_mma_live_reference_multi_iteration(harness):
         x, xr = ops.x.copy(), xr_new.copy()
         np.testing.assert_allclose(x, xr, rtol=0, atol=5e-8)
         np.testing.assert_allclose(offset, ref.offset, rtol=1e-14)
+
+
+def gcmma_history(ops, name, iters):
+    """Outer GCMMA iterations of a seeded analytic problem with the product's driver; shared with the GPU test."""
+    from make_golden_opt_inputs import gcmma_problem
+    from pymoto_b200.optimizers import gcmma_design_update
+
+    n, x0, responses = gcmma_problem(name)
+    as_np = (lambda a: a) if isinstance(ops.x, np.ndarray) else (lambda a: a.cpu().numpy())
+    to_ops = (lambda a: np.ascontiguousarray(a)) if isinstance(ops.x, np.ndarray) else ops.from_numpy
+    offset = to_ops(np.full(n, 0.5))
+    opt = dict(DEFAULTS, version=2007, a=np.zeros(ops.m), c=np.full(ops.m, 1e3), d=np.ones(ops.m))
+    x, xold1, xold2, xs, gs, rhos, nev = x0.copy(), None, None, [], [], [], []
+    for _ in range(iters):
+        gk, dg = responses(x)
+        count = [0]
+
+        def evaluate(xc):
+            count[0] += 1
+            return responses(as_np(xc))[0]
+
+        xd = to_ops(x)
+        if xold1 is not None and xold2 is not None:
+            ops.asymptotes(xd, to_ops(xold1), to_ops(xold2), offset, opt["asyincr"], opt["asydecr"], opt["asybound"])
+        r = gcmma_design_update(ops, xd, gk, [to_ops(row) for row in dg], offset, 0.0, 1.0, 0.1, opt, evaluate, maxit=20)
+        xold2, xold1 = xold1, x.copy()
+        x = as_np(ops.x).copy()
+        xs.append(x); gs.append(r["g"]); rhos.append(r["rho"]); nev.append(count[0])
+    return np.array(xs), np.array(gs), np.array(rhos), np.array(nev), as_np(offset)
+
+
+def check_gcmma_history(name, got):
+    g = load("gcmma")
+    xs, gs, rhos, nev, offset = got
+    assert np.array_equal(nev, g[name + "_nev"])  # same number of inner iterations in every outer iteration
+    np.testing.assert_allclose(rhos, g[name + "_rho"], rtol=1e-6)
+    np.testing.assert_allclose(gs, g[name + "_g"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(xs[0], g[name + "_x"][0], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(xs, g[name + "_x"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(offset, g[name + "_offset"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["gcmma_m2", "gcmma_unconstrained"])
+def test_gcmma_host_arithmetic_vs_reference_history(harness, name):
+    """GCMMA: the product's inner-iteration driver (rho initialisation / update, conservative-approximation test) on the host
+    harness against six outer iterations of pym.MMA(mmaversion="GCMMA") on a non-convex analytic problem."""
+    from make_golden_opt_inputs import GCMMA_CASES
+
+    n, nresp = GCMMA_CASES[name]
+    check_gcmma_history(name, gcmma_history(HostOps(harness, n, max(1, nresp - 1)), name, 6))
+
+
+def test_network_cones_and_slice_selection():
+    """slice_network (pymoto/common/optimizers.py:55-72): only the modules between the variables and the responses run."""
+    import pymoto_b200 as pmb
+    from pymoto_b200.optimizers import select_network
+
+    calls = []
+
+    def mod(tag, fn):
+        class M(pmb.Module):
+            def __call__(self, *a):
+                calls.append(tag)
+                return fn(*a)
+
+        M.__name__ = tag
+        return M()
+
+    sx, sother = pmb.Signal("x", state=np.arange(4.0)), pmb.Signal("o", state=np.ones(3))
+    fn = pmb.Network()
+    with fn:
+        sa = mod("A", lambda x: 2 * x)(sx)
+        sb = mod("B", lambda o: o + 1)(sother)          # does not depend on x
+        sg = mod("G", lambda a: float(a.sum()))(sa)
+        sunused = mod("U", lambda a: a * 3)(sa)          # depends on x, response does not depend on it
+        sh = mod("H", lambda a, b: float(a.sum() + b.sum()))(sa, sb)
+    assert [type(m).__name__ for m in fn.get_input_cone(sx)] == ["A", "G", "U", "H"]
+    assert [type(m).__name__ for m in fn.get_output_cone(sg)] == ["A", "G"]
+    sub = select_network(fn, [sx], [sg], slice_network=True)
+    assert [type(m).__name__ for m in sub] == ["A", "G"]
+    assert [type(m).__name__ for m in select_network(fn, [sx], [sh], True)] == ["A", "H"]  # B feeds H but does not depend on x
+    assert select_network(fn, [sx], [sg], False) is fn
+    calls.clear()
+    sub.response()
+    assert calls == ["A", "G"]
+    with pytest.raises(RuntimeError):
+        select_network(fn, [sother], [sg], True)
+    with fn:
+        assert select_network(None, [sx], [sg]) is fn
+    if not pmb.core.HAVE_PYMOTO:
+        with pytest.raises(RuntimeError):
+            select_network(None, [sx], [sg])
 
 
 def test_mma_constructor_contract_without_gpu():
