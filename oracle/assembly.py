@@ -172,17 +172,20 @@ def datamap_closed_form(grid: Grid, ndof, indptr):
 
 
 class Assembler:
-    """Oracle restatement of ``AssembleGeneral`` for one square element matrix, CSR output."""
+    """Oracle restatement of ``AssembleGeneral`` for square element matrices (one, or a list with one scaling vector each,
+    assembly.py:245-253) and an optional constant matrix added after the boundary conditions (:294-295), CSR output."""
 
-    def __init__(self, grid: Grid, element_matrix, bc=None, bcdiagval=None, closed_form=True):
+    def __init__(self, grid: Grid, element_matrix, bc=None, bcdiagval=None, closed_form=True, add_constant=None):
         self.grid = grid
-        self.Ke = np.asarray(element_matrix, dtype=float)
+        self.Kes = [np.asarray(m, dtype=float) for m in (element_matrix if isinstance(element_matrix, (list, tuple)) else [element_matrix])]
+        self.Ke = self.Kes[0]
+        self.add_constant = add_constant
         self.ndof = self.Ke.shape[0] // grid.elemnodes
         self.n = grid.nnodes * self.ndof
         self.bc = None if bc is None else np.asarray(bc).ravel()
         self.bcdiagval = bcdiagval
         if self.bc is not None and bcdiagval is None:
-            self.bcdiagval = np.max(self.Ke)  # assembly.py:94-98
+            self.bcdiagval = np.max(sum(self.Kes[1:], self.Kes[0]))  # assembly.py:94-98 (maximum of the SUM of the matrices)
         if closed_form:
             self.indptr, self.indices = pattern_closed_form(grid, self.ndof)
             self.datamap = datamap_closed_form(grid, self.ndof, self.indptr)
@@ -200,13 +203,20 @@ class Assembler:
             self.datamap = self.datamap.copy()
             self.datamap[bad] = self.bcadd[0]
 
-    def __call__(self, x):
-        scaled = (self.Ke.ravel()[None, :] * np.asarray(x).ravel()[:, None]).ravel()  # assembly.py:257
+    def __call__(self, *xs):
+        assert len(xs) == len(self.Kes)  # assembly.py:241-242
+        scaled = None
+        for x, Ke in zip(xs, self.Kes):  # assembly.py:250-257: the scaled element matrices are added BEFORE the scatter
+            term = (Ke.ravel()[None, :] * np.asarray(x).ravel()[:, None]).ravel()
+            scaled = term if scaled is None else scaled + term
         data = np.zeros(self.indices.size)
         np.add.at(data, self.datamap, scaled)  # assembly.py:267-268
         if self.bc is not None:
             data[self.bcadd] = self.bcdiagval  # assembly.py:270-272
-        return sps.csr_matrix((data, self.indices, self.indptr), shape=(self.n, self.n))  # assembly.py:275
+        mat = sps.csr_matrix((data, self.indices, self.indptr), shape=(self.n, self.n))  # assembly.py:275
+        if self.add_constant is not None:
+            mat = mat + self.add_constant  # assembly.py:294-295
+        return mat
 
     def sensitivity(self, u, v):
         """dx_e = u[dofs_e]^T Ke v[dofs_e] with u, v zeroed at bc (assembly.py:301-303, 311-314)."""
@@ -216,4 +226,5 @@ class Assembler:
             u[self.bc] = 0.0
             v[self.bc] = 0.0
         dc = self.grid.dofconn(self.ndof)
-        return np.einsum("Ai,ij,Aj->A", u[dc], self.Ke, v[dc])
+        dx = [np.einsum("Ai,ij,Aj->A", u[dc], Ke, v[dc]) for Ke in self.Kes]
+        return dx[0] if len(dx) == 1 else dx

@@ -1,6 +1,6 @@
 """Golden fixtures for the optimiser rows from the UNMODIFIED reference (pyMOTO at /root/reference).
 
-    python tests/golden/make_golden_opt.py [oc] [mma] [subsolv] [gcmma] [vti]
+    python tests/golden/make_golden_opt.py [oc] [mma] [subsolv] [gcmma] [asm] [vti]
 
   ref_oc_mbb100x50.npz   10 OC iterations of the 2-D MBB 100x50 problem (BASELINE configs[0]; pym.OC.step)
   ref_mma_mbb60x30.npz   8 MMA2007 iterations, 2-D MBB 60x30, compliance objective (Scaling 100) + volume constraint (Scaling 10)
@@ -8,6 +8,8 @@
   ref_mma_subsolv.npz    single subproblems (pym.MMA.mmasub on seeded data): m = 1, 2, unconstrained, MMA1987, vector bounds
   ref_gcmma.npz          6 GCMMA outer iterations (pym.MMA(mmaversion="GCMMA").step through a Network) of two seeded analytic problems:
                          designs, responses, rho, number of response evaluations per outer iteration
+  ref_asm_multi.npz      pym.AssembleGeneral with several element matrices / bc / add_constant on seeded inputs: the assembled matrix
+                         (dense) and the sensitivities of a dyad
   ref_vti.npz            bytes of VoxelDomain.write_to_vti files (2-D with vector padding, 3-D, block vectors)
 """
 import os
@@ -20,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from _refimport import import_reference  # noqa: E402
-from make_golden_opt_inputs import GCMMA_CASES, SUBSOLV_CASES, gcmma_problem, subsolv_inputs, vti_inputs  # noqa: E402
+from make_golden_opt_inputs import ASM_CASES, asm_inputs, GCMMA_CASES, SUBSOLV_CASES, gcmma_problem, subsolv_inputs, vti_inputs  # noqa: E402
 
 pym = import_reference()
 assert pym is not None, "reference not found at /root/reference"
@@ -139,6 +141,24 @@ def gcmma_case(iters=6):
     np.savez_compressed(os.path.join(HERE, "ref_gcmma.npz"), **out)
 
 
+def asm_case():
+    out = {}
+    for name in ASM_CASES:
+        p = asm_inputs(name)
+        d = pym.VoxelDomain(*p["shape"])
+        mod = pym.AssembleGeneral(d, p["mats"] if len(p["mats"]) > 1 else p["mats"][0], bc=p["bc"], add_constant=p["const"])
+        sigs = [pym.Signal(f"x{i}", state=x.copy()) for i, x in enumerate(p["xs"])]
+        sK = mod(*sigs)
+        K = sK.state
+        sK.sensitivity = pym.DyadicMatrix(p["u"].copy(), p["v"].copy())
+        mod.sensitivity()
+        out[name + "_K"] = K.toarray()
+        for i, s in enumerate(sigs):
+            out[f"{name}_dx{i}"] = np.asarray(s.sensitivity)
+        print("asm", name, "shape", K.shape, "nnz", K.nnz, "bcdiagval", mod.bcdiagval)
+    np.savez_compressed(os.path.join(HERE, "ref_asm_multi.npz"), **out)
+
+
 def vti_case():
     out = {}
     for name in ("2d", "3d", "block"):
@@ -153,7 +173,7 @@ def vti_case():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["oc", "mma", "subsolv", "gcmma", "vti"]
+    what = sys.argv[1:] or ["oc", "mma", "subsolv", "gcmma", "asm", "vti"]
     if "oc" in what:
         oc_case()
     if "mma" in what:
@@ -163,5 +183,7 @@ if __name__ == "__main__":
         subsolv_case()
     if "gcmma" in what:
         gcmma_case()
+    if "asm" in what:
+        asm_case()
     if "vti" in what:
         vti_case()

@@ -59,6 +59,50 @@ def gcmma_problem(name):
 
     return n, x0, responses
 
+ASM_CASES = {
+    # name: (shape, dofs per node, number of element matrices, Dirichlet dofs?, add_constant?)
+    "hex_two_const": ((5, 4, 3), 3, 2, True, True),
+    "quad_const": ((7, 5, 0), 1, 1, False, True),
+    "quad_three_bc": ((6, 5, 0), 2, 3, True, False),
+    "hex_two_thermal": ((4, 4, 5), 1, 2, True, False),
+}
+
+
+def asm_inputs(name):
+    """Seeded inputs of an AssembleGeneral with several element matrices and / or a constant matrix (assembly.py:38-47,
+    245-253, 294-295): element matrices, scaling vectors, Dirichlet dofs, the constant (scipy CSR inside the node stencil:
+    a random diagonal plus couplings between the dofs of a node and to the next node in x), and a dyad (u, v) for the sensitivity."""
+    import scipy.sparse as sps
+
+    shape, ndof, nmat, with_bc, with_const = ASM_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    nx, ny, nz = shape
+    dim = 3 if nz > 0 else 2
+    nel = nx * ny * max(nz, 1)
+    nnodes = (nx + 1) * (ny + 1) * (nz + 1)
+    n = nnodes * ndof
+    ld = (2 ** dim) * ndof
+    mats = []
+    for _ in range(nmat):
+        r = rng.standard_normal((ld, ld))
+        mats.append(r @ r.T / ld + 0.1 * rng.standard_normal((ld, ld)))  # general (not symmetric) real matrices
+    xs = [0.05 + rng.random(nel) for _ in range(nmat)]
+    bc = np.unique(rng.integers(0, n, max(3, n // 12))) if with_bc else None
+    const = None
+    if with_const:
+        diag = sps.diags(0.5 + rng.random(n))
+        r = np.arange(n - ndof)
+        nxt = sps.coo_matrix((0.1 * rng.standard_normal(r.size), (r, r + ndof)), shape=(n, n))  # next node in x (or wraps to the
+        keep = ((r // ndof) % (nx + 1)) != nx                                                   # next row: dropped)
+        nxt = sps.coo_matrix((nxt.data[keep], (nxt.row[keep], nxt.col[keep])), shape=(n, n))
+        const = (diag + nxt + 0.5 * nxt.T).tocsr()
+        if ndof > 1:
+            rr = np.arange(n - 1)
+            same = (rr // ndof) == ((rr + 1) // ndof)
+            const = (const + sps.coo_matrix((0.2 * rng.standard_normal(int(same.sum())), (rr[same], rr[same] + 1)), shape=(n, n))).tocsr()
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    return dict(shape=shape, ndof=ndof, mats=mats, xs=xs, bc=bc, const=const, u=u, v=v)
+
 
 def vti_inputs(name):
     rng = np.random.default_rng(len(name))

@@ -85,3 +85,81 @@ def test_gcmma_class_through_network_vs_reference_history(pmb, host):
         x = xnew
     assert other[0] == 0  # slice_network: the module the responses do not depend on never ran
     assert isinstance(sx.state, np.ndarray) == host
+
+
+# ------------------------------------------------------------------------------------------------ several element matrices / add_constant
+@pytest.mark.parametrize("name", ["hex_two_const", "quad_const", "quad_three_bc", "hex_two_thermal"])
+def test_assembly_several_matrices_and_constant_vs_reference(pmb, name):
+    """pymoto_b200.AssembleGeneral with a list of element matrices, Dirichlet dofs and add_constant against the unmodified
+    reference's output on seeded inputs (assembly.py:245-253, 294-295).  The device sums separately assembled matrices, the
+    reference sums scaled element matrices before scattering: equal to rounding (1e-14 of the largest entry), not bit for bit."""
+    import torch
+    from _golden import load
+    from make_golden_opt_inputs import asm_inputs
+
+    g = load("asm_multi")
+    p = asm_inputs(name)
+    dom = pmb.VoxelDomain(*p["shape"])
+    mats = p["mats"] if len(p["mats"]) > 1 else p["mats"][0]
+    for device_inputs in (False, True):
+        asm = pmb.AssembleGeneral(dom, mats, bc=p["bc"], add_constant=p["const"])
+        sigs = [pmb.Signal(f"x{i}", state=(torch.as_tensor(x, device="cuda") if device_inputs else x.copy())) for i, x in enumerate(p["xs"])]
+        sK = asm(*sigs)
+        K = sK.state
+        assert K.generator is None  # applied from the assembled values on every level
+        want = g[name + "_K"]
+        np.testing.assert_allclose(K.toarray(), want, rtol=0, atol=1e-14 * np.abs(want).max())
+        # the operator products use the summed values (row statistics re-derived from them)
+        xv = np.random.default_rng(1).standard_normal(K.shape[0])
+        np.testing.assert_allclose((K @ xv), want @ xv, rtol=0, atol=1e-12 * np.abs(want @ xv).max())
+        np.testing.assert_allclose(K.diagonal(), np.diag(want), rtol=0, atol=1e-14 * np.abs(want).max())
+        sK.sensitivity = pmb.DeviceDyad(torch.as_tensor(p["u"], device="cuda"), torch.as_tensor(p["v"], device="cuda"))
+        asm.sensitivity()
+        for i, s in enumerate(sigs):
+            assert torch.is_tensor(s.sensitivity) == device_inputs
+            got = s.sensitivity.cpu().numpy() if device_inputs else s.sensitivity
+            np.testing.assert_allclose(got, g[f"{name}_dx{i}"], rtol=1e-12, atol=1e-13)
+    with pytest.raises(ValueError):
+        asm(*sigs, sigs[0])
+    if len(p["mats"]) > 1:
+        with pytest.raises(ValueError):
+            pmb.AssembleGeneral(dom, [p["mats"][0], p["mats"][1][:-1]])
+
+
+def test_two_material_solve_with_constant_vs_scipy(pmb):
+    """A two-material stiffness (two element matrices, two density fields) plus a constant diagonal spring matrix solved with
+    CG + geometric multigrid on assembled values (no matrix-free level 0, two-pass Galerkin) against scipy on the oracle's matrix;
+    sensitivities of the compliance to both fields against the oracle's adjoint expressions."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+
+    import oracle
+    from oracle import Grid
+    from oracle.chain import cantilever
+
+    gr = Grid(16, 8, 8)
+    ndof, bc, f = cantilever(gr)
+    dom = pmb.VoxelDomain(16, 8, 8)
+    rng = np.random.default_rng(5)
+    K1, K2 = oracle.assembly.stiffness_element(gr), oracle.assembly.stiffness_element(gr, e_modulus=0.3, poisson_ratio=0.2)
+    x1, x2 = 0.2 + 0.8 * rng.random(gr.nel), 0.1 + rng.random(gr.nel)
+    spring = sps.diags(1e-3 * rng.random(gr.nnodes * 3)).tocsr()
+    Ko = oracle.assembly.Assembler(gr, [K1, K2], bc=bc, add_constant=spring)
+    Kref = Ko(x1, x2)
+    uref = spla.spsolve(Kref.tocsc(), f)
+    s1, s2 = pmb.Signal("x1", state=x1.copy()), pmb.Signal("x2", state=x2.copy())
+    with pmb.Network() as fn:
+        asm = pmb.AssembleGeneral(dom, [K1, K2], bc=bc, add_constant=spring)
+        sK = asm(s1, s2)
+        cg = pmb.solvers.CG(preconditioner=pmb.solvers.auto_multigrid(dom, min_size=2)[0], tol=1e-10)
+        su = pmb.LinSolve(hermitian=True, solver=cg)(sK, f)
+        sc = pmb.Compliance()(su, f)
+    u = su.state
+    assert np.linalg.norm(Kref @ u - f) <= 1e-8 * np.linalg.norm(f)
+    np.testing.assert_allclose(u, uref, rtol=0, atol=1e-7 * np.abs(uref).max())
+    assert 0 < cg.iterations < 40
+    sc.sensitivity = 1.0
+    fn.sensitivity()
+    d1, d2 = Ko.sensitivity(-uref, uref)  # dc/dx_i = -u_e^T K_i u_e
+    np.testing.assert_allclose(s1.sensitivity, d1, rtol=1e-6, atol=1e-8 * np.abs(d1).max())
+    np.testing.assert_allclose(s2.sensitivity, d2, rtol=1e-6, atol=1e-8 * np.abs(d2).max())
