@@ -43,7 +43,12 @@ class DensityFilter(Module):
             dy, dx = np.meshgrid(rng, rng, indexing="ij")
             dz = np.zeros_like(dx)
         w = np.maximum(0.0, radius - np.sqrt(dx * dx + dy * dy + dz * dz))
-        self._wtab = dv.to_device(np.ascontiguousarray(w.ravel()))
+        # the kernel's window is trimmed to the offsets that carry weight (an integer radius r leaves the outermost shell of the
+        # (2r+1)^dim window at exactly 0: 27 of 125 slots at r = 2); w * x = +-0 terms never change a sum, the bits stay
+        nzw = w > 0
+        self._dk = dk = int(max(np.abs(dx[nzw]).max(), np.abs(dy[nzw]).max(), np.abs(dz[nzw]).max())) if nzw.any() else 0
+        keep = (np.abs(dx) <= dk) & (np.abs(dy) <= dk) & (np.abs(dz) <= dk)
+        self._wtab = dv.to_device(np.ascontiguousarray(w[keep]))
         # row sums Hs = H @ 1 (filter.py:251) by the same stencil with unit input
         self.Hs = dv.empty(self.nel)
         self._apply(None, None, self.Hs)
@@ -60,7 +65,7 @@ class DensityFilter(Module):
             self._xbuf[self._pad: self._pad + self.nel] = inp
             self._ctx.comm.exchange(self._xbuf, self._pad, self.nel, self._lay, width=self.d)
             inp = self._xbuf[self._pad: self._pad + self.nel]
-        _lib.call("pmb_filter_apply", self.grid, self._e0, self.nlayers, self.d, dv.ptr(self._wtab), dv.ptr(inp), dv.ptr(hs),
+        _lib.call("pmb_filter_apply", self.grid, self._e0, self.nlayers, self._dk, dv.ptr(self._wtab), dv.ptr(inp), dv.ptr(hs),
                   dv.ptr(out), dv.stream())
         return out
 
