@@ -103,10 +103,9 @@ struct ParCfg {
   static constexpr int PITCH = (ROW + 2 + 1) / 2 * 2;        // + 16-byte hull, even: every row starts 16-byte aligned
   static constexpr int PLANE = (EY + 1) * PITCH;
   static constexpr int OC = NDOF * NT;                       // one per-thread array: [c][ty][tx]
-  static constexpr int KB = 8 * ParBlocks<NDOF>::NB;
   // plane ring + 2 corner-exchange buffers (3 corners) + the values carried from layer to layer (top-face result and
-  // x / y-transformed top plane, 4 parity patterns each) + the packed blocks
-  static constexpr size_t SMEM = sizeof(double) * (PAR_RING * PLANE + (2 * 3 + 8) * OC + KB);
+  // x / y-transformed top plane, 4 parity patterns each)
+  static constexpr size_t SMEM = sizeof(double) * (PAR_RING * PLANE + (2 * 3 + 8) * OC);
 };
 
 // n / d for a normal, finite d by Newton iterations on the hardware reciprocal seed: the compiler's IEEE division spends
@@ -161,9 +160,15 @@ __global__ void __launch_bounds__(PAR_EX* EY, MINB)
   // values carried from layer to layer, as double2 (parity patterns px = 0 / 1 of one (py, c)) -> 128-bit shared accesses:
   double2* sc = reinterpret_cast<double2*>(so + 2 * 3 * OC);   // [2 NDOF][NT] top-face result of the layer below (parity basis)
   double2* sb = sc + 2 * OC;                                    // [2 NDOF][NT] x / y-transformed node plane under the layer
-  // the packed blocks: read by every thread in every step as broadcast 128-bit loads (as kernel parameters the compiler
-  // hoists the 48 values out of the layer loop, they do not fit the uniform registers and end up in local memory)
-  const double2* skb = reinterpret_cast<const double2*>(sb + 2 * OC);
+  // The packed blocks stay in the kernel-parameter constant bank and reach the FP64 pipe through uniform registers (SASS: LDCU.64
+  // + DFMA R, R, UR): no shared-memory instruction.  Read with plain indices the compiler hoists the 48 values out of the layer
+  // loop, they do not fit the uniform registers and end up in local memory (1.7 GB of traffic per launch, measured); the index
+  // used below carries a term of the loop counter that is always 0 but not provably so, which keeps the loads inside the loop.
+  // (First kept in shared memory and read as broadcast LDS.128: 24 more shared-memory instructions per thread and layer on a
+  // kernel whose top stall reasons are the shared-memory queue and the barrier -- 0.253 -> 0.225 ms at 256x128x128, ndof 3;
+  // carrying the per-thread values in registers instead of shared memory on top of that gains nothing: at 128 registers it
+  // spills, and with 12 or 8 warps per SM the kernel is 20 - 30 % slower.)
+  const double2* ckb = reinterpret_cast<const double2*>(kb.v);
   __shared__ __align__(8) uint64_t full_bar[R];
   __shared__ double wred[3][NT / 32];
 
@@ -174,7 +179,6 @@ __global__ void __launch_bounds__(PAR_EX* EY, MINB)
   const long long Dx = (long long)(reinterpret_cast<uintptr_t>(x) >> 3);
 
   for (int p = tid; p < R * PLANE; p += NT) su[p] = 0.0;   // stale-but-finite contract
-  for (int p = tid; p < C::KB; p += NT) const_cast<double*>(reinterpret_cast<const double*>(skb))[p] = kb.v[p];
   if (tid == 0) {
     for (int q = 0; q < R; ++q) mbar_init(&full_bar[q], 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(PAR_EX* EY, MINB)
       double kv[NB + 1];
 #pragma unroll
       for (int i = 0; i < (NB + 1) / 2; ++i) {
-        const double2 k2 = skb[(q * NB) / 2 + i];      // NB even (ndof 3) or q * NB read pairwise (ndof 1, see below)
+        const double2 k2 = ckb[(q * NB) / 2 + i + (t >> 28)];   // NB even (ndof 3) or q * NB read pairwise (ndof 1, see below)
         kv[2 * i] = k2.x;
         kv[2 * i + 1] = k2.y;
       }
