@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(PAR_EX* EY, MINB)
     const double s_next = (eok && el + 1 >= elo && el + 1 < ehi) ? __ldg(sp) : 0.0;
     const bool emit = owner && t > 0;                // plane el >= kA is owned by this CTA
     sh0 ^= pk;                                       // shift of row ty in the top plane
-    if (emit && NDOF > 1) {   // (scalar problems: the extra instructions cost more than the prefetch hides, measured 1 - 2 %)
+    if (emit) {
       if (MODE != EMODE_SPMV) prefetch_l1(b + r0), prefetch_l1(b + r0 + NDOF - 1);
       if (MODE == EMODE_JACOBI) prefetch_l1(diag + r0), prefetch_l1(diag + r0 + NDOF - 1);
       if (partials && dotv) prefetch_l1(dotv + r0), prefetch_l1(dotv + r0 + NDOF - 1);
