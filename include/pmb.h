@@ -308,7 +308,7 @@ int pmb_simp_bwd(long long n, double xmin, int p, const double* y, const double*
  * m = number of general constraints (1..PMB_MMA_MAXM; an unconstrained problem passes one dummy row of zeros like the
  * reference does).  P, Q: (m+1) x n row-major.  All `out` arrays are DEVICE memory, sums first then maxima; every pass is a
  * deterministic two-stage reduction over ws (pmb_mma_ws_doubles() doubles, zero-initialised once by the caller). */
-#define PMB_MMA_MAXM 3
+#define PMB_MMA_MAXM 6
 typedef struct {
   double s;        /* value for every variable ...                  */
   const double* v; /* ... unless v != NULL: per-variable device array */

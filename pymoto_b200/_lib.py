@@ -53,7 +53,7 @@ class ElemOp(C.Structure):
                 ("brickflags", C.c_void_p), ("variant", C.c_int)]
 
 
-MMA_MAXM = 3  # PMB_MMA_MAXM
+MMA_MAXM = 6  # PMB_MMA_MAXM
 MAX_LEVELS = 12  # PMB_MAX_LEVELS
 
 

@@ -14,7 +14,7 @@
 #endif
 
 #ifndef PMB_MMA_MAXM
-#define PMB_MMA_MAXM 3  // general constraints m handled by the device path; P and Q have m+1 <= 4 rows
+#define PMB_MMA_MAXM 6  // general constraints m handled by the device path; P and Q have m+1 <= 7 rows
 #endif
 
 struct MmaVar {  // everything of ONE design variable the Newton kernels need

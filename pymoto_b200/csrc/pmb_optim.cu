@@ -10,7 +10,7 @@
 
 static constexpr int OPT_BLOCKS = 592;  // 4 CTAs per SM on 148 SMs
 static constexpr int OPT_THREADS = 256;
-static constexpr int OPT_MAXRED = 16;   // sums + maxima per pass
+static constexpr int OPT_MAXRED = 2 * PMB_MMA_MAXM + PMB_MMA_MAXM * PMB_MMA_MAXM;   // sums + maxima per pass (Newton sums: 2m + m^2)
 
 extern "C" long long pmb_mma_ws_doubles(void) { return 8 + (long long)OPT_MAXRED * OPT_BLOCKS; }
 
@@ -149,6 +149,9 @@ static int check_vecs(const pmb_mma_vecs* v, const char* who) {
     case 1: { constexpr int M = 1; CALL; } break;                                   \
     case 2: { constexpr int M = 2; CALL; } break;                                   \
     case 3: { constexpr int M = 3; CALL; } break;                                   \
+    case 4: { constexpr int M = 4; CALL; } break;                                   \
+    case 5: { constexpr int M = 5; CALL; } break;                                   \
+    case 6: { constexpr int M = 6; CALL; } break;                                   \
     default: return pmb_set_error("pmb_mma: m=%d not in 1..%d", m, PMB_MMA_MAXM);   \
   }
 

@@ -171,7 +171,7 @@ class MmaDeviceOps:
         self.t = {nm: dv.empty(n * (m + 1) if nm in ("P", "Q") else n) for nm in _lib.MmaVecs.NAMES}
         self.vecs = _lib.MmaVecs(*[self.t[nm].data_ptr() for nm in _lib.MmaVecs.NAMES])
         self.ws = dv.zeros(_lib.query("pmb_mma_ws_doubles"))
-        self.out = dv.empty(16)
+        self.out = dv.empty(2 * _lib.MMA_MAXM + _lib.MMA_MAXM ** 2 + 8)  # the largest pass returns 2m + m^2 sums
         self._C = C
         # design vector distributed over z-slabs: n is this rank's share, the reduced sums / maxima are made global
         self.n_global = int(_allreduce(torch.tensor([float(n)], dtype=torch.float64, device=self.out.device))[0].item())

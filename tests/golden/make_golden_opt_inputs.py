@@ -9,6 +9,8 @@ SUBSOLV_CASES = {
     "unconstrained": (200, 1, "MMA2007", False),
     "m1_1987": (400, 2, "MMA1987", False),
     "m3_vecbounds": (250, 4, "MMA2007", True),
+    "m5": (350, 6, "MMA2007", False),
+    "m6_vecbounds": (280, 7, "MMA2007", True),
 }
 
 

@@ -129,7 +129,8 @@ static void est_t(long long n, HVecs a, const double* xval, HBound xmin, HBound 
 
 #define DISPATCH(m, CALL) \
   switch (m) { case 1: { constexpr int M = 1; CALL; } break; case 2: { constexpr int M = 2; CALL; } break; \
-               case 3: { constexpr int M = 3; CALL; } break; default: return 1; }
+               case 3: { constexpr int M = 3; CALL; } break; case 4: { constexpr int M = 4; CALL; } break; \
+               case 5: { constexpr int M = 5; CALL; } break; case 6: { constexpr int M = 6; CALL; } break; default: return 1; }
 
 extern "C" {
 int hmma_asymptotes(long long n, const double* x, const double* xold1, const double* xold2, double asyincr, double asydecr, double asybound,

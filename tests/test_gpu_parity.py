@@ -1050,9 +1050,9 @@ def test_linsolve_multiple_rhs_and_finite_difference(pmb):
 
 # ------------------------------------------------------------------------------------------------ MMA on the device (next row f3)
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds"])
+@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds", "m5", "m6_vecbounds"])
 def test_mma_device_update_vs_reference_golden(pmb, name):
-    """pmb_mma_* kernels + the host Newton driver against pym.MMA.step on seeded subproblems (m = 1, 2, 3 constraints,
+    """pmb_mma_* kernels + the host Newton driver against pym.MMA.step on seeded subproblems (m = 1, 2, 3, 5, 6 constraints,
     unconstrained, MMA1987, vector bounds): asymptotes to rounding, new design within 2e-9 absolute."""
     import sys
 

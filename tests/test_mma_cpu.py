@@ -46,7 +46,7 @@ class HostOps:
         self.lib, self.n, self.m = lib, n, m
         self.t = {nm: np.zeros(n * (m + 1) if nm in ("P", "Q") else n) for nm in NAMES}
         self.vecs = HVecs(*[self.t[nm].ctypes.data for nm in NAMES])
-        self.out = np.zeros(16)
+        self.out = np.zeros(64)
 
     @property
     def x(self):
@@ -129,7 +129,7 @@ def run_update(ops_factory, p):
     return ops, offset, lam, its
 
 
-@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds"])
+@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds", "m5", "m6_vecbounds"])
 def test_mma_update_host_arithmetic_vs_reference_golden(harness, name):
     """asymptotes + set-up + primal-dual Newton solve against pym.MMA.step on the same seeded subproblem."""
     from make_golden_opt_inputs import subsolv_inputs

@@ -191,7 +191,7 @@ def test_oc_oracle_against_golden():
     np.testing.assert_allclose(hist, g["history"][:4], rtol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds"])
+@pytest.mark.parametrize("name", ["m1", "m2", "unconstrained", "m1_1987", "m3_vecbounds", "m5", "m6_vecbounds"])
 def test_mma_oracle_against_golden(name):
     """Oracle MMA update (numpy restatement of pymoto/common/mma.py) against pym.MMA.step on seeded subproblems."""
     from make_golden_opt_inputs import subsolv_inputs
