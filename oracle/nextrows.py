@@ -98,8 +98,10 @@ class MMAOracle:
       asymptote offsets   mma.py:120-140    mmasub (bounds, P, Q, rhs)   mma.py:170-244
       subsolv             mma.py:246-474    (primal-dual Newton with the (m+1)x(m+1) reduced system and a residual line search)
 
-    Supports MMA1987 / MMA2007 (not GCMMA), scalar or vector xmin / xmax / move; ``step(x, g, dg)`` takes the responses
-    g (first = objective) and their sensitivities dg (rows) and returns the new design."""
+    Supports MMA1987 / MMA2007 / GCMMA, scalar or vector xmin / xmax / move; ``step(x, g, dg)`` takes the responses
+    g (first = objective) and their sensitivities dg (rows) and returns the new design.  GCMMA (mma.py:104-160, 232-242) needs the
+    responses at the inner candidates: pass ``evaluate(x) -> g``; ``step`` then returns the design accepted by the inner loop and
+    leaves the responses evaluated last in ``self.g_last`` (the reference returns them), ``self.rho``, ``self.inner``."""
 
     def __init__(self, n, nresp, move=0.1, xmin=0.0, xmax=1.0, version="MMA2007", a0=1.0, epsimin=1e-10, ccoef=1e3, albefa=0.1,
                  asyinit=0.5, asyincr=1.2, asydecr=0.7, asybound=10.0):
@@ -114,19 +116,36 @@ class MMAOracle:
         self.xold1 = self.xold2 = None
         self.newton_iterations = 0
 
-    def step(self, x, g, dg):
+    def step(self, x, g, dg, evaluate=None, gcmma_maxit=20):
         g, dg = np.atleast_1d(np.asarray(g, dtype=float)), np.atleast_2d(np.asarray(dg, dtype=float))
         if self.xold1 is not None and self.xold2 is not None:  # :120-140
             zzz = (x - self.xold1) * (self.xold1 - self.xold2)
             self.offset[zzz > 0] *= self.asyincr
             self.offset[zzz < 0] *= self.asydecr
             self.offset = np.clip(self.offset, 1 / self.asybound ** 2, self.asybound)
-        xnew = self._mmasub(x, g, dg, rho=1e-5)
+        if "gcmma" not in self.version.lower():
+            xnew = self._mmasub(x, g, dg, rho=1e-5)
+        else:  # :142-160 inner iterations around the outer design x with its responses gk = g and sensitivities dg
+            gk, xnew, self.inner = g, None, 0
+            for it in range(gcmma_maxit):
+                if it > 0:
+                    g = np.atleast_1d(np.asarray(evaluate(xnew), dtype=float))
+                    if np.all(self.gest >= g):
+                        break
+                    delta = (g - self.gest) / self.dk  # :152-154
+                    upd = delta > 0
+                    self.rho[upd] = np.minimum(1.1 * (self.rho + delta), 10 * self.rho)[upd]
+                else:
+                    self.rho = 0.1 / self.n * np.sum(self.dx * np.abs(dg), axis=1)  # :151
+                xnew = self._mmasub(x, gk, dg, rho=self.rho)
+                self.inner += 1
+            self.g_last = g
         self.xold2, self.xold1 = self.xold1, x.copy()
         return xnew
 
     def _mmasub(self, xval, g, dg, rho):
-        if g.size == 1:  # :172-175 dummy constraint
+        unconstrained = g.size == 1
+        if unconstrained:  # :172-175 dummy constraint
             g, dg = np.hstack((g, -1.0)), np.vstack((dg, np.zeros(self.n)))
         shift = self.offset * self.dx
         self.low, self.upp = xval - shift, xval + shift
@@ -135,11 +154,21 @@ class MMAOracle:
         gp, gm, dx2 = np.maximum(dg, 0), np.maximum(-dg, 0), shift ** 2
         if "1987" in self.version:
             P, Q = dx2 * gp, dx2 * gm
+        elif "gcmma" in self.version.lower():  # :213-216 (a single response's rho also serves the dummy row: the reference broadcasts)
+            rr = np.maximum(np.asarray(rho, dtype=float).reshape(-1, 1), 1e-6)
+            P = dx2 * (1.001 * gp + 0.001 * gm + rr / self.dx)
+            Q = dx2 * (0.001 * gp + 1.001 * gm + rr / self.dx)
         else:
             P = dx2 * (1.001 * gp + 0.001 * gm + rho / self.dx)
             Q = dx2 * (0.001 * gp + 1.001 * gm + rho / self.dx)
         rhs = P @ (1 / shift) + Q @ (1 / shift) - g
-        return self._subsolv(self.epsimin * np.sqrt(self.m + self.n), self.low, self.upp, alfa, beta, P, Q, rhs[1:], xval)
+        xmma = self._subsolv(self.epsimin * np.sqrt(self.m + self.n), self.low, self.upp, alfa, beta, P, Q, rhs[1:], xval)
+        # :236-239 values of the approximations at the subproblem solution and the step measure of the rho update
+        self.gest = np.sum(P / (self.upp - xmma) + Q / (xmma - self.low), axis=1) - rhs
+        if unconstrained:
+            self.gest = self.gest[[0]]
+        self.dk = np.sum((self.upp - self.low) * (xmma - xval) ** 2 / ((self.upp - xmma) * (xmma - self.low) * self.dx))
+        return xmma
 
     def _subsolv(self, epsimin, low, upp, alfa, beta, P, Q, b, x0):
         m, a0, a, c, d = self.m, self.a0, self.a, self.c, self.d

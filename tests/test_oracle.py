@@ -223,3 +223,30 @@ def test_assembly_several_matrices_and_constant_against_golden(name):
     dx = asm.sensitivity(p["u"], p["v"])
     for i, d in enumerate(dx if isinstance(dx, list) else [dx]):
         np.testing.assert_allclose(d, g[f"{name}_dx{i}"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["gcmma_m2", "gcmma_unconstrained"])
+def test_gcmma_oracle_against_golden(name):
+    """The numpy GCMMA restatement (inner iterations, rho initialisation / update, conservative-approximation test) against six
+    outer iterations of pym.MMA(mmaversion="GCMMA") on the seeded non-convex problems: same number of response evaluations."""
+    from make_golden_opt_inputs import GCMMA_CASES, gcmma_problem
+    from oracle.nextrows import MMAOracle
+
+    g = load("gcmma")
+    n, x0, responses = gcmma_problem(name)
+    opt = MMAOracle(n, GCMMA_CASES[name][1], version="GCMMA")
+    x = x0.copy()
+    for it in range(6):
+        count = [0]
+
+        def evaluate(xc):
+            count[0] += 1
+            return responses(xc)[0]
+
+        gk, dg = responses(x)
+        x = opt.step(x, gk, dg, evaluate=evaluate)
+        assert count[0] == int(g[name + "_nev"][it])
+        np.testing.assert_allclose(opt.rho, g[name + "_rho"][it], rtol=1e-8)
+        np.testing.assert_allclose(opt.g_last, g[name + "_g"][it], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(x, g[name + "_x"][it], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(opt.offset, g[name + "_offset"], rtol=1e-13)
